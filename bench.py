@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: MFCC + log-mel extraction throughput in audio-seconds per second.
+
+Workload (BASELINE.json configs[1]): an ESC-50-shaped synthetic set, 2000 clips x 5 s mono at
+44.1 kHz per GPU, frame 1024 / hop 512, 40 mels, 13 MFCCs; one "step" = one pass of the fused
+feature kernel over the whole set, producing MFCC [2000,429,13] and log-mel [2000,429,40].
+
+    python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA kernels via the C ABI)
+    python bench.py --impl reference [...]                     the CPU arm (oracle port, all host threads)
+
+Under torchrun (N > 1) every rank owns its own 2000-clip shard (clips are independent: weak
+scaling, no data-path collective); the time is the max over ranks and `value` the aggregate.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+SR, CLIP_LEN, FL, HOP, N_MELS, N_MFCC = 44_100, 220_500, 1024, 512, 40, 13
+CLIP_SECONDS = CLIP_LEN / SR
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--clips", type=int, default=2000, help="clips per GPU (ESC-50 has 2000)")
+    ap.add_argument("--outputs", default="mfcc+log_mel", choices=("mfcc", "log_mel", "mfcc+log_mel"))
+    ap.add_argument("--kernel", default="auto", choices=("auto", "generic", "warp8"))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_clip(outputs: str, n_frames: int) -> int:
+    """every sample read once + features written once."""
+    b = 4 * CLIP_LEN
+    if "mfcc" in outputs:
+        b += 4 * n_frames * N_MFCC
+    if "log_mel" in outputs:
+        b += 4 * n_frames * N_MELS
+    return b
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(self.period)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_arm(args, n_frames: int):
+    """The CPU implementation of the path (oracle port of src/dsp, all host threads)."""
+    from dsp_final_b200 import synth
+    from oracle import oracle as O
+
+    cfg = O.OracleConfig(SR, FL, HOP, n_mels=N_MELS, n_mfcc=N_MFCC)
+    cores = O.max_threads()
+    want = tuple(n for n in ("mfcc", "log_mel") if n in args.outputs)
+    per_step = max(cores, 8)
+    clips = synth.host_clips(min(per_step, 64), seed=1234)
+    if clips.shape[0] < per_step:
+        clips = np.concatenate([clips] * ((per_step + clips.shape[0] - 1) // clips.shape[0]))[:per_step]
+    return O, cfg, cores, want, clips
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_frames = 1 + (CLIP_LEN - FL) // HOP
+    O, cfg, cores, want, clips = cpu_arm(args, n_frames)
+    per_step = clips.shape[0]
+    t0 = time.perf_counter()
+    O.features_batch(clips, cfg, want=want)                       # calibration step (counts as warm-up)
+    one = time.perf_counter() - t0
+    # keep the whole run within a few minutes whatever K is
+    budget = 150.0
+    steps, warm = args.steps, max(0, args.warmup - 1)
+    if one * (steps + warm) > budget:
+        shrink = max(1, int(per_step * budget / (one * (steps + warm))))
+        clips = clips[:shrink]
+        per_step = clips.shape[0]
+    for _ in range(warm):
+        O.features_batch(clips, cfg, want=want)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.features_batch(clips, cfg, want=want)
+    dt = time.perf_counter() - t0
+    value = per_step * CLIP_SECONDS * steps / dt
+    sample = f"{per_step} synthetic 5 s clips per step x {steps} steps, C port of src/dsp (complex128 radix-2), OpenMP over clips"
+    line = {
+        "impl": "reference", "metric": "mfcc_logmel_audio_seconds_per_second", "value": value,
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"ESC-50-shaped synthetic set, frame {FL} hop {HOP}, {args.outputs} (bounded sample)",
+                   "outputs": args.outputs},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from dsp_final_b200 import _lib, synth
+    from dsp_final_b200.batch import features_batch
+    from dsp_final_b200.dist import init_process_group
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+    from dsp_final_b200.plan import get_plan
+
+    _lib.load()
+    _lib.require_device()
+    rank, world, local = init_process_group()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg = MfccConfig(sample_rate=SR, frame_length=FL, hop_length=HOP, n_mels=N_MELS, n_mfcc=N_MFCC)
+    plan = get_plan(cfg, local, args.kernel)
+    n_frames = plan.num_frames(CLIP_LEN)
+    want = tuple(n for n in ("mfcc", "log_mel") if n in args.outputs)
+    b = args.clips
+    lib = _lib.load()
+
+    # inputs resident in HBM before the timed region (1.76 GB per GPU: larger than the 126 MB L2)
+    clips = synth.device_clips(b, seed=1234, device=dev, first=rank * b)
+    mf = torch.empty((b, n_frames, N_MFCC), dtype=torch.float32, device=dev) if "mfcc" in want else None
+    lm = torch.empty((b, n_frames, N_MELS), dtype=torch.float32, device=dev) if "log_mel" in want else None
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        _lib.check(lib.dspx_features(plan.handle, clips.data_ptr(), b, CLIP_LEN, clips.stride(0),
+                                     lm.data_ptr() if lm is not None else None,
+                                     mf.data_ptr() if mf is not None else None, None, stream.cuda_stream),
+                   "dspx_features")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * b * CLIP_SECONDS * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant (only) kernel of the step
+    bytes_per_launch = b * algorithmic_bytes_per_clip(args.outputs, n_frames)
+    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per_launch / avg_launch_s / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(plan.kernel, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": f"feat_{plan.kernel}",
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                "note": "co-bound by FP32 issue + shared-memory bandwidth (DESIGN.md): 2.67 MFLOP per audio-second"}
+
+    # end to end through the host-buffer C ABI: pinned host clips in, host features out
+    e2e = None
+    if args.e2e_steps > 0:
+        h_clips = torch.empty((b, CLIP_LEN), dtype=torch.float32, pin_memory=True)
+        h_clips.copy_(clips)
+        h_mf = torch.empty((b, n_frames, N_MFCC), dtype=torch.float32, pin_memory=True) if mf is not None else None
+        h_lm = torch.empty((b, n_frames, N_MELS), dtype=torch.float32, pin_memory=True) if lm is not None else None
+        torch.cuda.synchronize(dev)
+
+        def e2e_step():
+            _lib.check(lib.dspx_features_host(plan.handle, h_clips.data_ptr(), b, CLIP_LEN, CLIP_LEN,
+                                              h_lm.data_ptr() if h_lm is not None else None,
+                                              h_mf.data_ptr() if h_mf is not None else None, None),
+                       "dspx_features_host")
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        d2h = (h_mf.numel() * 4 if h_mf is not None else 0) + (h_lm.numel() * 4 if h_lm is not None else 0)
+        e2e = {"value": world * b * CLIP_SECONDS * args.e2e_steps / dt, "unit": "audio-s/s",
+               "h2d_bytes_per_step": b * CLIP_LEN * 4, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "api": "dspx_features_host (pinned host buffers in and out)"}
+        # the host path and the device path run the same kernel: results must be identical
+        if h_mf is not None:
+            assert torch.equal(h_mf[:8], mf[:8].cpu()), "host-pipeline result differs from device-path result"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # parity spot check + CPU baseline (rank 0, N = 1 only for the baseline)
+    from oracle import oracle as O
+
+    ocfg = O.OracleConfig(SR, FL, HOP, n_mels=N_MELS, n_mfcc=N_MFCC)
+    sel = [0, b // 2, b - 1]
+    host_sel = clips[sel].cpu().numpy()
+    ref = O.features_batch(host_sel, ocfg, want=want)
+    parity = {}
+    if mf is not None:
+        parity["mfcc_rel_err"] = O.relative_error(mf[sel].cpu().numpy(), ref["mfcc"])
+    if lm is not None:
+        parity["log_mel_rel_err"] = O.relative_error(lm[sel].cpu().numpy(), ref["log_mel"])
+    parity["clips_checked"] = len(sel)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = O.max_threads()
+        host = synth.host_clips(min(max(cores, 8), 64), seed=1234)
+        t0 = time.perf_counter()
+        O.features_batch(host[: max(1, min(cores, host.shape[0]))], ocfg, want=want)
+        one = time.perf_counter() - t0
+        reps = max(1, int(args.cpu_seconds / max(one, 1e-3)))
+        n_cal = max(1, min(cores, host.shape[0]))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.features_batch(host[:n_cal], ocfg, want=want)
+        dtc = time.perf_counter() - t0
+        cpu_baseline = {"value": n_cal * reps * CLIP_SECONDS / dtc, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                        "sample": f"{n_cal * reps} synthetic 5 s clips ({dtc:.1f} s), C port of src/dsp (complex128 radix-2), OpenMP over clips"}
+
+    line = {
+        "metric": "mfcc_logmel_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ESC-50-shaped synthetic set: {b} clips x 5 s @44.1 kHz per GPU, frame {FL} hop {HOP}, "
+                               f"{N_MELS} mels, {N_MFCC} MFCC (BASELINE.json configs[1])",
+                   "outputs": args.outputs, "clips_per_gpu": b, "kernel": plan.kernel,
+                   "l2_policy": "inputs_larger_than_l2 (1.76 GB per pass vs 126 MB L2)", "parallelism": f"clip-sharded x{world}"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps,
+        "clocks": clocks, "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+// emu.cu -- TEST-ONLY host replay of the kernels' phase functions.
+//
+// The feature kernels are written as __host__ __device__ "phase" functions over a
+// flat item index, separated by barriers.  This file replays those same functions
+// on the CPU, one item after another, so that the index arithmetic, table layouts
+// and numerics of the CUDA source can be checked against the oracle in the dev
+// container (which has nvcc but no GPU).  It is built into libdspx_emu.so, which
+// only tests/ load; libdspx.so (the product) contains none of this and has no CPU
+// path.
+#include <vector>
+
+#include "dspx_internal.cuh"
+#include "tables.cuh"
+#include "feat_generic.cuh"
+#include "feat_warp8.cuh"
+
+namespace dspx {
+void set_error(const char *, ...) {}
+const char *get_error() { return ""; }
+}  // namespace dspx
+
+using namespace dspx;
+
+struct EmuTables {
+    HostTables t;
+    std::vector<float> window, dct2;
+    std::vector<float2> tw;
+    int P = 0, M = 0, n_bins = 0, take_feat = 0, take_stft = 0, n_stages = 0;
+    int radix[16] = {0};
+};
+
+static int emu_build(const dspx_config *cfg, EmuTables &e)
+{
+    const int nfft_raw = cfg->n_fft > 0 ? cfg->n_fft : cfg->frame_length;
+    e.P = (int)next_pow_two(nfft_raw);
+    if (e.P < 16 || e.P > 8192) return DSPX_EUNSUPPORTED;
+    e.M = e.P / 2;
+    e.n_bins = e.M + 1;
+    e.take_feat = cfg->frame_length < e.P ? cfg->frame_length : e.P;
+    e.take_stft = cfg->frame_length < nfft_raw ? cfg->frame_length : nfft_raw;
+    int m = e.M;
+    while (m > 1) {
+        if (m % 4 == 0) { e.radix[e.n_stages++] = 4; m /= 4; }
+        else { e.radix[e.n_stages++] = 2; m /= 2; }
+    }
+    if (!build_window(cfg->window, cfg->frame_length, e.t.window)) return DSPX_EINVAL;
+    const double f_max = cfg->f_max < 0.0 ? cfg->sample_rate / 2.0 : cfg->f_max;
+    build_filterbank(cfg->n_mels, e.P, cfg->sample_rate, cfg->f_min, f_max, e.t);
+    build_dct2(cfg->n_mfcc, cfg->n_mels, e.t.dct2);
+    e.window.assign(e.t.window.begin(), e.t.window.end());
+    e.dct2.assign(e.t.dct2.begin(), e.t.dct2.end());
+    e.tw.resize(e.P);
+    for (int j = 0; j < e.P; j++) {
+        const double a = -2.0 * M_PI * (double)j / (double)e.P;
+        e.tw[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    return DSPX_OK;
+}
+
+extern "C" {
+
+// Replays feat_generic_kernel.  stft_out != NULL selects the complex-spectrum mode.
+int emu_features_generic(const dspx_config *cfg, const float *clips, int64_t n_clips, int64_t clip_len,
+                         int64_t clip_stride, int stft_mode, int stft_pre, float *logmel, float *mfcc, float *stft_out,
+                         int frames_per_cta_override)
+{
+    EmuTables e;
+    int rc = emu_build(cfg, e);
+    if (rc != DSPX_OK) return rc;
+    if (clip_len < cfg->frame_length) return DSPX_EINVAL;
+    const int64_t T = 1 + (clip_len - cfg->frame_length) / cfg->hop_length;
+    GenParams p{};
+    p.clips = clips;
+    p.n_clips = n_clips;
+    p.clip_len = clip_len;
+    p.clip_stride = clip_stride;
+    p.n_frames = T;
+    p.frame_length = cfg->frame_length;
+    p.hop = cfg->hop_length;
+    p.take = stft_mode ? e.take_stft : e.take_feat;
+    p.P = e.P;
+    p.M = e.M;
+    p.n_bins = e.n_bins;
+    p.n_stages = e.n_stages;
+    for (int i = 0; i < 16; i++) p.radix[i] = e.radix[i];
+    p.n_mels = cfg->n_mels;
+    p.n_mfcc = cfg->n_mfcc;
+    int G = 1024 / e.M;
+    if (G < 1) G = 1;
+    if (G > 16) G = 16;
+    p.G = G;
+    const int64_t groups = (T + G - 1) / G;
+    int64_t gpc = frames_per_cta_override > 0 ? (frames_per_cta_override + G - 1) / G : groups;
+    p.frames_per_cta = (int)(gpc * G);
+    p.ctas_per_clip = (int)((T + p.frames_per_cta - 1) / p.frames_per_cta);
+    p.pre = stft_mode ? (stft_pre && cfg->pre_emphasis > 0.0) : (cfg->pre_emphasis > 0.0);
+    p.alpha = (float)cfg->pre_emphasis;
+    p.window = e.window.data();
+    p.tw = e.tw.data();
+    p.fb_start = e.t.fb_start.data();
+    p.fb_cnt = e.t.fb_cnt.data();
+    p.fb_off = e.t.fb_off.data();
+    p.fb_w = e.t.fb_w.data();
+    p.dct2 = e.dct2.data();
+    p.logmel = logmel;
+    p.mfcc = mfcc;
+    p.stft = stft_mode ? reinterpret_cast<float2 *>(stft_out) : nullptr;
+
+    std::vector<unsigned char> smem(gen_smem_bytes(G, p.M, p.n_mels));
+    const GenSmem sm = gen_carve(smem.data(), G, p.M, p.n_mels);
+    for (int64_t blk = 0; blk < n_clips * p.ctas_per_clip; blk++) {
+        const int64_t clip_idx = blk / p.ctas_per_clip, chunk = blk - clip_idx * p.ctas_per_clip;
+        const float *clip = clips + clip_idx * clip_stride;
+        const int64_t t_begin = chunk * p.frames_per_cta;
+        int64_t t_end = t_begin + p.frames_per_cta;
+        if (t_end > T) t_end = T;
+        for (int64_t t0 = t_begin; t0 < t_end; t0 += G) {
+            for (int i = 0; i < G * p.M; i++) gen_phase_load(p, sm, clip, t0, i);
+            float2 *in = sm.a, *out = sm.b;
+            int ns = 1;
+            for (int s = 0; s < p.n_stages; s++) {
+                for (int i = 0; i < G * (p.M / p.radix[s]); i++) gen_phase_stage(p, in, out, s, ns, i);
+                ns *= p.radix[s];
+                float2 *tmp = in; in = out; out = tmp;
+            }
+            float *pw = reinterpret_cast<float *>(out);
+            for (int i = 0; i < G * (p.M / 2 + 1); i++) gen_phase_post(p, in, pw, clip_idx, t0, i);
+            if (!p.stft) {
+                for (int i = 0; i < G * p.n_mels * GEN_MEL_PARTS; i++) gen_phase_melpart(p, pw, sm.part, i);
+                for (int i = 0; i < G * p.n_mels; i++) gen_phase_logmel(p, sm.part, sm.lm, clip_idx, t0, i);
+                if (p.mfcc)
+                    for (int i = 0; i < G * p.n_mfcc; i++) gen_phase_dct(p, sm.lm, clip_idx, t0, i);
+            }
+        }
+    }
+    return DSPX_OK;
+}
+
+}  // extern "C"

@@ -442,8 +442,9 @@ int orc_features_batch(const float *clips, int64_t n_clips, int64_t len, int64_t
 /*
  * ---- src/retrieval/retrieval.py:46-49 (cosine_similarity) + :65 (top-k) ----
  * q [nq,d], db [ndb,d] float64.  Rows are scaled by 1/(||row|| + 1e-10) (eps
- * added to the norm, not under the root), scores are plain left-to-right dot
- * products in float64 (no FMA contraction), and the k best per query are
+ * added to the norm, not under the root), scores are left-to-right chains of
+ * IEEE fused multiply-adds in float64 (fma(): the same operation sequence the
+ * CUDA kernel issues, so scores match it bit for bit), and the k best per query are
  * returned in descending score order with ties broken by the LOWER database
  * index -- i.e. np.argsort(-sims, axis=1, kind="stable")[:, :k].  (The
  * reference's default introsort leaves tie order unspecified)
@@ -456,7 +457,7 @@ int orc_cosine_topk(const double *q, int64_t nq, const double *db, int64_t ndb, 
     if (!dbn) return ORC_ENOMEM;
     for (int64_t j = 0; j < ndb; j++) {
         double s = 0.0;
-        for (int c = 0; c < d; c++) s += db[j * d + c] * db[j * d + c];
+        for (int c = 0; c < d; c++) s = fma(db[j * d + c], db[j * d + c], s);
         double inv = sqrt(s) + 1e-10;
         for (int c = 0; c < d; c++) dbn[j * d + c] = db[j * d + c] / inv;
     }
@@ -471,13 +472,13 @@ int orc_cosine_topk(const double *q, int64_t nq, const double *db, int64_t ndb, 
         int32_t *bi = (int32_t *)malloc((size_t)k * sizeof(int32_t));
         if (!qn || !bs || !bi) { rc_all = ORC_ENOMEM; free(qn); free(bs); free(bi); continue; }
         double s = 0.0;
-        for (int c = 0; c < d; c++) s += q[i * d + c] * q[i * d + c];
+        for (int c = 0; c < d; c++) s = fma(q[i * d + c], q[i * d + c], s);
         double inv = sqrt(s) + 1e-10;
         for (int c = 0; c < d; c++) qn[c] = q[i * d + c] / inv;
         int have = 0;
         for (int64_t j = 0; j < ndb; j++) {
             double acc = 0.0;
-            for (int c = 0; c < d; c++) acc += qn[c] * dbn[j * d + c];
+            for (int c = 0; c < d; c++) acc = fma(qn[c], dbn[j * d + c], acc);
             /* sorted insert; strict > keeps the earlier (lower) index first on ties */
             if (have < k || acc > bs[have - 1]) {
                 int pos = have < k ? have : k - 1;
