@@ -36,8 +36,8 @@ def _as_host_clips(clips) -> np.ndarray:
         a = a[None, :]
     if a.ndim != 2:
         raise ValueError("clips must be [n_clips, n_samples]")
-    if a.dtype != np.float32 or a.strides[1] != 4 or a.strides[0] % 4 or a.strides[0] < 0:
-        a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.dtype != np.float32 or a.strides[1] != 4 or a.strides[0] % 4 or a.strides[0] < 4 * a.shape[1]:
+        a = np.ascontiguousarray(a, dtype=np.float32)      # also normalises the 0 stride of a[None, :]
     return a
 
 
@@ -97,7 +97,7 @@ def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int
     lm = np.empty((b, t, plan.n_mels), np.float32) if "log_mel" in want else None
     mf = np.empty((b, t, plan.n_mfcc), np.float32) if "mfcc" in want else None
     em = np.empty((b, 2 * plan.n_mfcc), np.float32) if "embed" in want else None
-    _lib.check(lib.dspx_features_host(plan.handle, x.ctypes.data, b, length, x.strides[0] // 4,
+    _lib.check(lib.dspx_features_host(plan.handle, x.ctypes.data, b, length, max(x.strides[0] // 4, length),
                                       lm.ctypes.data if lm is not None else None,
                                       mf.ctypes.data if mf is not None else None,
                                       em.ctypes.data if em is not None else None), "dspx_features_host")
@@ -154,7 +154,8 @@ def stft_batch(clips, frame_length: int, hop_length: int, window: str = "hann", 
     b, length = x.shape
     t = plan.num_frames(length)
     out = np.empty((b, t, plan.n_bins), np.complex64)
-    _lib.check(lib.dspx_stft_host(plan.handle, x.ctypes.data, b, length, x.strides[0] // 4, pre, out.ctypes.data),
+    _lib.check(lib.dspx_stft_host(plan.handle, x.ctypes.data, b, length, max(x.strides[0] // 4, length), pre,
+                                  out.ctypes.data),
                "dspx_stft_host")
     return out
 

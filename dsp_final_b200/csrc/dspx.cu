@@ -93,6 +93,7 @@ static void plan_free_device(dspx_plan *p)
     cudaFree(p->d_bin_wfall);
     cudaFree(p->d_bin_wrise);
     cudaFree(p->d_fast_tables);
+    warp8_release(p);
     if (p->host_pipe) {
         auto *hp = static_cast<HostPipe *>(p->host_pipe);
         hp->release();
@@ -153,6 +154,13 @@ static int launch_generic(const dspx_plan *pl, const float *clips, int64_t n_cli
     feat_generic_kernel<<<(unsigned)grid, GEN_THREADS, smem, st>>>(gp);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
+}
+
+int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
+                            int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st)
+{
+    return launch_generic(pl, clips, n_clips, clip_len, clip_stride, T, pl->take_feat,
+                          pl->cfg.pre_emphasis > 0.0 ? 1 : 0, logmel, mfcc, nullptr, st);
 }
 
 static int launch_embed(const float *feats, int64_t n_clips, int64_t T, int C, float *out, cudaStream_t st)

@@ -97,6 +97,7 @@ struct dspx_plan {
     float *d_bin_wfall = nullptr, *d_bin_wrise = nullptr;
     void *d_fast_tables = nullptr;      // packed tables of the warp8 kernel (feat_warp8.cuh)
     size_t fast_tables_bytes = 0;
+    void *fast_host = nullptr;          // host-side descriptor of those tables (W8PlanData)
     // host pipeline state (pinned staging, streams), created lazily by the *_host calls
     void *host_pipe = nullptr;
 };

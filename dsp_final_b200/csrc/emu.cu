@@ -136,4 +136,65 @@ int emu_features_generic(const dspx_config *cfg, const float *clips, int64_t n_c
     return DSPX_OK;
 }
 
+// Replays feat_warp8_kernel: one "warp" at a time, each phase run for lanes 0..31 in turn
+// (a __syncwarp() separates the phases on the device).
+int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_clips, int64_t clip_len,
+                       int64_t clip_stride, float *logmel, float *mfcc)
+{
+    EmuTables e;
+    int rc = emu_build(cfg, e);
+    if (rc != DSPX_OK) return rc;
+    dspx_plan pl;
+    pl.cfg = *cfg;
+    pl.P = e.P;
+    pl.M = e.M;
+    pl.n_bins = e.n_bins;
+    pl.host = e.t;
+    if (!warp8_supported(&pl) || clip_len < cfg->frame_length) return DSPX_EUNSUPPORTED;
+    if (clip_stride & 1) return DSPX_EUNSUPPORTED;
+    std::vector<float> blob;
+    W8Tables tb{};
+    warp8_build_tables(&pl, blob, tb);
+    const int64_t T = 1 + (clip_len - cfg->frame_length) / cfg->hop_length;
+    W8Params p{};
+    p.clips = clips;
+    p.n_clips = n_clips;
+    p.clip_stride = clip_stride;
+    p.n_frames = T;
+    p.pairs_per_clip = (T + 1) / 2;
+    p.n_items = n_clips * p.pairs_per_clip;
+    p.hop = cfg->hop_length;
+    p.pre = cfg->pre_emphasis > 0.0 ? 1 : 0;
+    p.n_mels = cfg->n_mels;
+    p.n_mfcc = cfg->n_mfcc;
+    p.alpha = (float)cfg->pre_emphasis;
+    p.tb = tb;
+    p.tables = blob.data();
+    p.logmel = logmel;
+    p.mfcc = mfcc;
+    std::vector<float> warp_smem(w8_warp_floats(tb, p.n_mels) + 4, 0.f);
+    W8Ctx c;
+    // 16-byte align the warp tile like the device carve-up does
+    float *ws = warp_smem.data();
+    while (reinterpret_cast<uintptr_t>(ws) & 15) ws++;
+    w8_carve(blob.data(), ws, tb, c);
+    c.alpha = p.alpha;
+    c.pre = p.pre;
+    c.n_mels = p.n_mels;
+    c.n_mfcc = p.n_mfcc;
+    c.rounds = tb.rounds;
+    std::vector<W8Power> pw(32);
+    for (int64_t item = 0; item < p.n_items; item++) {
+        w8_set_item(p, c, item);
+        for (int lane = 0; lane < 32; lane++) w8_pass1(c, lane);
+        for (int lane = 0; lane < 32; lane++) w8_pass2(c, lane);
+        for (int lane = 0; lane < 32; lane++) w8_pass3(c, lane, pw[lane]);
+        for (int lane = 0; lane < 32; lane++) w8_store_power(c, lane, pw[lane]);
+        for (int lane = 0; lane < 32; lane++) w8_mel_items(c, lane);
+        for (int lane = 0; lane < 32; lane++) w8_logmel(c, lane);
+        for (int lane = 0; lane < 32; lane++) w8_dct(c, lane);
+    }
+    return DSPX_OK;
+}
+
 }  // extern "C"

@@ -1,12 +1,547 @@
-// feat_warp8.cuh -- placeholder until the warp-autonomous radix-8 kernel lands.
+// feat_warp8.cuh -- the headline kernel: warp-autonomous, radix-8, packed-f32x2 fused
+// pre-emphasis -> frame -> window -> FFT -> |X|^2 -> mel -> log -> DCT for frame_length =
+// n_fft = 1024 (the configuration BASELINE.json quotes its metric on).
+//
+// Reference ops replaced: src/dsp/mfcc.py:86-109 (log_mel_spectrogram, mfcc) with everything
+// they call: stft.py:27-56 (framing, window), fft.py:27-77 (rfft), mfcc.py:32-83 (mel, DCT).
+//
+// Design (DESIGN.md "warp8 kernel" has the long form):
+//  * One WARP owns two consecutive frames of a clip at a time and never synchronises with any
+//    other warp: no __syncthreads in the main loop, only __syncwarp between FFT passes.
+//  * The two frames ride in the two halves of Blackwell's packed FP32 instructions (FFMA2 /
+//    FADD2 / FMUL2, sm_100+): every arithmetic instruction, shared-memory access and address
+//    computation serves both frames; twiddles enter as scalar-broadcast operands.
+//  * 1024 real samples are packed into a 512-point complex FFT = 8 x 8 x 8: three in-register
+//    radix-8 passes, two exchanges through an 8 KB per-warp shared-memory tile addressed with an
+//    XOR swizzle (128-bit accesses, conflict-free in all three access patterns).
+//  * The last pass is laid out so that lane u holds bins k = u (mod 64) AND their mirror
+//    images 512-k, so the packed-real split and |X|^2 need no further exchange.
+//  * Samples are read straight from global memory (coalesced 8-byte loads of 256-byte rows; the
+//    50% frame overlap is served by L1/L2), pre-emphasised with rounded mul + rounded sub exactly
+//    like NumPy's float32 evaluation, and windowed in registers.
+//  * mel projection = balanced (filter, part) work items over the power spectrum in shared
+//    memory; log; DCT from a shared-memory table; features stored straight to HBM.
+//
+// The per-lane work between two __syncwarp()s is written as __host__ __device__ "lane phase"
+// functions so that csrc/emu.cu can replay the exact same source on the CPU (tests only).
 #pragma once
+
+#include <algorithm>
+
 #include "dspx_internal.cuh"
+
 namespace dspx {
-inline bool warp8_supported(const dspx_plan *) { return false; }
-inline int warp8_prepare(dspx_plan *) { return DSPX_EUNSUPPORTED; }
-inline int launch_warp8(const dspx_plan *, const float *, int64_t, int64_t, int64_t, int64_t, float *, float *, cudaStream_t)
+
+constexpr int W8_WARPS = 8;               // warps per CTA
+constexpr int W8_XFLOATS = 2048 + 16;     // per-warp exchange tile: 512 x (reA,reB,imA,imB); reused for P[513]
+constexpr int W8_MEL_J = 8;               // bins per mel work item
+
+// ---- packed two-frame arithmetic (x = frame A, y = frame B) ------------------------------
+#if defined(__CUDA_ARCH__)
+DSPX_HD float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+DSPX_HD float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+DSPX_HD float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+DSPX_HD float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+DSPX_HD float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DSPX_HD float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+DSPX_HD float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+DSPX_HD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+DSPX_HD float2 bc2(float s) { return make_float2(s, s); }
+DSPX_HD float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+// (re, im) *= (c + i s) for both frames; c, s scalar
+DSPX_HD void cmul2(float2 &re, float2 &im, float c, float s)
 {
-    set_error("warp8 kernel not built");
-    return DSPX_EUNSUPPORTED;
+    const float2 cc = bc2(c), ss = bc2(s);
+    const float2 r = fma2(neg2(im), ss, mul2(re, cc));
+    im = fma2(im, cc, mul2(re, ss));
+    re = r;
 }
+
+// 8-point forward DFT in registers (decimation in frequency), natural order in and out.
+// 52 packed adds + 4 packed muls.
+DSPX_HD void dft8(float2 (&re)[8], float2 (&im)[8])
+{
+    const float h = 0.70710678118654752440f;
+    float2 ar[8], ai[8];
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        ar[n] = add2(re[n], re[n + 4]);
+        ai[n] = add2(im[n], im[n + 4]);
+        ar[n + 4] = sub2(re[n], re[n + 4]);
+        ai[n + 4] = sub2(im[n], im[n + 4]);
+    }
+    // odd branch twiddles: a5 *= (1 - i)/sqrt2, a6 *= -i, a7 *= (-1 - i)/sqrt2
+    {
+        const float2 r5 = add2(ar[5], ai[5]), i5 = sub2(ai[5], ar[5]);
+        ar[5] = mul2(r5, bc2(h));
+        ai[5] = mul2(i5, bc2(h));
+        const float2 r6 = ai[6], i6 = neg2(ar[6]);
+        ar[6] = r6;
+        ai[6] = i6;
+        const float2 r7 = sub2(ai[7], ar[7]), i7 = add2(ar[7], ai[7]);
+        ar[7] = mul2(r7, bc2(h));
+        ai[7] = mul2(i7, bc2(-h));
+    }
+#pragma unroll
+    for (int o = 0; o < 2; o++) {          // o = 0: even outputs from a0..a3, o = 1: odd from a4..a7
+        const int b = 4 * o;
+        const float2 s02r = add2(ar[b], ar[b + 2]), s02i = add2(ai[b], ai[b + 2]);
+        const float2 d02r = sub2(ar[b], ar[b + 2]), d02i = sub2(ai[b], ai[b + 2]);
+        const float2 s13r = add2(ar[b + 1], ar[b + 3]), s13i = add2(ai[b + 1], ai[b + 3]);
+        const float2 d13r = sub2(ai[b + 1], ai[b + 3]);                 // (c1 - c3) * (-i)
+        const float2 d13i = sub2(ar[b + 3], ar[b + 1]);
+        re[o] = add2(s02r, s13r);
+        im[o] = add2(s02i, s13i);
+        re[o + 2] = add2(d02r, d13r);
+        im[o + 2] = add2(d02i, d13i);
+        re[o + 4] = sub2(s02r, s13r);
+        im[o + 4] = sub2(s02i, s13i);
+        re[o + 6] = sub2(d02r, d13r);
+        im[o + 6] = sub2(d02i, d13i);
+    }
+}
+
+// exchange-tile address (in float4 units) of element (k_a, x, c): x = b before pass 2, k_b after
+DSPX_HD int w8_addr(int ka, int x, int c) { return ((ka * 8 + x) << 3) | (c ^ ka); }
+
+struct W8Tables {            // offsets (in floats) into the packed table blob / shared memory
+    int win, tw1, tw2, ptw, mi, mw, filt, dct2, total;
+    int n_slots, rounds;
+};
+
+struct W8Params {
+    const float *clips;
+    int64_t n_clips, clip_stride, n_frames, pairs_per_clip, n_items;
+    int hop, pre, n_mels, n_mfcc;
+    float alpha;
+    W8Tables tb;
+    const float *tables;     // global copy of the blob
+    float *logmel, *mfcc;    // either may be null
+};
+
+struct W8Ctx {               // everything one warp needs for one frame pair
+    const float2 *win, *tw1, *tw2, *ptw;
+    const int4 *mi;
+    const float *mw;
+    const int2 *filt;
+    const float *dct2;
+    float4 *xbuf;
+    float2 *pbuf, *part, *lm;
+    const float *clip;       // first sample of the clip
+    int64_t sA, sB;          // first sample of frame A / B inside the clip
+    float alpha;
+    int pre, n_mels, n_mfcc, rounds, validB;
+    float *logmelA, *logmelB, *mfccA, *mfccB;   // rows of the two frames (null when not requested)
+};
+
+struct W8Power {             // |X|^2 of the bins one lane owns, carried across the syncwarp
+    float2 lo[9], hi[9];
+};
+
+DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, W8Ctx &c)
+{
+    c.win = reinterpret_cast<const float2 *>(tables_smem + tb.win);
+    c.tw1 = reinterpret_cast<const float2 *>(tables_smem + tb.tw1);
+    c.tw2 = reinterpret_cast<const float2 *>(tables_smem + tb.tw2);
+    c.ptw = reinterpret_cast<const float2 *>(tables_smem + tb.ptw);
+    c.mi = reinterpret_cast<const int4 *>(tables_smem + tb.mi);
+    c.mw = tables_smem + tb.mw;
+    c.filt = reinterpret_cast<const int2 *>(tables_smem + tb.filt);
+    c.dct2 = tables_smem + tb.dct2;
+    c.xbuf = reinterpret_cast<float4 *>(warp_smem);
+    c.pbuf = reinterpret_cast<float2 *>(warp_smem);
+    c.part = reinterpret_cast<float2 *>(warp_smem + W8_XFLOATS);
+    c.lm = c.part + tb.n_slots;
+}
+
+DSPX_HD int w8_warp_floats(const W8Tables &tb, int n_mels) { return (W8_XFLOATS + 2 * tb.n_slots + 2 * n_mels + 3) & ~3; }
+
+// ---- phase A: load, pre-emphasis, window, radix-8 over a, twiddle, store -----------------
+DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
+{
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int tid = lane + 32 * s;
+        float2 re[8], im[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const int n = 128 * a + 2 * tid;
+            const float *pa = c.clip + c.sA + n, *pb = c.clip + c.sB + n;
+            const float2 xa = *reinterpret_cast<const float2 *>(pa);
+            const float2 xb = *reinterpret_cast<const float2 *>(pb);
+            float2 y0 = make_float2(xa.x, xb.x), y1 = make_float2(xa.y, xb.y);
+            if (c.pre) {
+                const float2 pv = make_float2(c.sA + n > 0 ? pa[-1] : 0.f, c.sB + n > 0 ? pb[-1] : 0.f);
+                const float2 al = bc2(c.alpha);
+                const float2 t0 = mul2(pv, al), t1 = mul2(y0, al);      // rounded products ...
+                y1 = sub2(y1, t1);                                      // ... then rounded differences
+                y0 = sub2(y0, t0);
+            }
+            const float2 w = c.win[(s * 8 + a) * 32 + lane];            // (0.5 w[n], 0.5 w[n+1])
+            re[a] = mul2(y0, bc2(w.x));
+            im[a] = mul2(y1, bc2(w.y));
+        }
+        dft8(re, im);
+        c.xbuf[w8_addr(0, tid >> 3, tid & 7)] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
+#pragma unroll
+        for (int ka = 1; ka < 8; ka++) {
+            const float2 w = c.tw1[(s * 7 + ka - 1) * 32 + lane];       // exp(-2 pi i tid ka / 512)
+            cmul2(re[ka], im[ka], w.x, w.y);
+            c.xbuf[w8_addr(ka, tid >> 3, tid & 7)] = make_float4(re[ka].x, re[ka].y, im[ka].x, im[ka].y);
+        }
+    }
+}
+
+// ---- phase B: radix-8 over b, in place, twiddle exp(-2 pi i c k_b / 64) ---------------------
+DSPX_HD void w8_pass2(const W8Ctx &c, int lane)
+{
+    const int cc = lane & 7;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int ka = (lane >> 3) + 4 * s;
+        float2 re[8], im[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const float4 v = c.xbuf[w8_addr(ka, b, cc)];
+            re[b] = make_float2(v.x, v.y);
+            im[b] = make_float2(v.z, v.w);
+        }
+        dft8(re, im);
+        c.xbuf[w8_addr(ka, 0, cc)] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
+#pragma unroll
+        for (int kb = 1; kb < 8; kb++) {
+            const float2 w = c.tw2[(kb - 1) * 8 + cc];
+            cmul2(re[kb], im[kb], w.x, w.y);
+            c.xbuf[w8_addr(ka, kb, cc)] = make_float4(re[kb].x, re[kb].y, im[kb].x, im[kb].y);
+        }
+    }
+}
+
+// packed-real split of one mirror pair (a = Z[k], b = Z[512-k]); the window carries the 1/2:
+//   E = a + conj b, O = -i (a - conj b), T = W^k O, |X[k]|^2 = |E + T|^2, |X[512-k]|^2 = |E - T|^2
+DSPX_HD void w8_split(float2 ar, float2 ai, float2 br, float2 bi, float2 w, float2 &plo, float2 &phi)
+{
+    const float2 er = add2(ar, br), ei = sub2(ai, bi);
+    const float2 orr = add2(ai, bi), oi = sub2(br, ar);
+    const float2 wr = bc2(w.x), wi = bc2(w.y);
+    const float2 tr = fma2(neg2(oi), wi, mul2(orr, wr));
+    const float2 ti = fma2(orr, wi, mul2(oi, wr));
+    const float2 xr = add2(er, tr), xi = add2(ei, ti);
+    const float2 yr = sub2(er, tr), yi = sub2(ei, ti);
+    plo = fma2(xi, xi, mul2(xr, xr));
+    phi = fma2(yi, yi, mul2(yr, yr));
+}
+
+DSPX_HD float2 sel2(bool p, float2 a, float2 b) { return p ? a : b; }
+
+// ---- phase C: radix-8 over c for residues j and 64-j, split, power ---------------------------
+DSPX_HD void w8_pass3(const W8Ctx &c, int lane, W8Power &pw)
+{
+    const bool l0 = lane == 0;
+    const int j1 = lane, j2 = l0 ? 32 : 64 - lane;
+    float2 r1[8], i1[8], r2[8], i2[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float4 v = c.xbuf[w8_addr(j1 & 7, j1 >> 3, q)];
+        r1[q] = make_float2(v.x, v.y);
+        i1[q] = make_float2(v.z, v.w);
+        const float4 u = c.xbuf[w8_addr(j2 & 7, j2 >> 3, q)];
+        r2[q] = make_float2(u.x, u.y);
+        i2[q] = make_float2(u.z, u.w);
+    }
+    dft8(r1, i1);          // Z[j1 + 64 m]
+    dft8(r2, i2);          // Z[j2 + 64 m]
+    // lanes 1..31: slot m pairs Z[lane + 64 m] with Z[512 - lane - 64 m] = D2[7 - m].
+    // lane 0 owns the self-mirrored residues 0 and 32: slots {0:(Z0,Z0) 1..3:(Z[64m],Z[512-64m])
+    // 4:(Z256,Z256) 5..7:(Z[32+64q],Z[480-64q]) q=0..2} and a ninth slot (Z224, Z288).
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        float2 ar = r1[m], ai = i1[m];
+        if (m >= 5) { ar = sel2(l0, r2[m - 5], ar); ai = sel2(l0, i2[m - 5], ai); }
+        const int b0 = m == 0 ? 0 : (m <= 4 ? 8 - m : 0);               // lane-0 partner index in D1 (m <= 4)
+        float2 br, bi;
+        if (m <= 4) { br = sel2(l0, r1[b0 & 7], r2[7 - m]); bi = sel2(l0, i1[b0 & 7], i2[7 - m]); }
+        else { br = sel2(l0, r2[12 - m], r2[7 - m]); bi = sel2(l0, i2[12 - m], i2[7 - m]); }
+        w8_split(ar, ai, br, bi, c.ptw[m * 32 + lane], pw.lo[m], pw.hi[m]);
+    }
+    if (l0) w8_split(r2[3], i2[3], r2[4], i2[4], c.ptw[8 * 32], pw.lo[8], pw.hi[8]);
+}
+
+DSPX_HD int w8_bin(int lane, int m)      // bin index of slot m
+{
+    const int k0[9] = {0, 64, 128, 192, 256, 32, 96, 160, 224};
+    return lane == 0 ? k0[m] : lane + 64 * m;
+}
+
+// ---- phase D: power spectrum to the (re-used) tile, natural bin order ---------------------------
+DSPX_HD void w8_store_power(const W8Ctx &c, int lane, const W8Power &pw)
+{
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int k = w8_bin(lane, m);
+        c.pbuf[k] = pw.lo[m];
+        c.pbuf[512 - k] = pw.hi[m];
+    }
+    if (lane == 0) { c.pbuf[224] = pw.lo[8]; c.pbuf[288] = pw.hi[8]; }
+}
+
+// ---- phase E: mel work items: 8 strided bins of one filter each ----------------------------------
+DSPX_HD void w8_mel_items(const W8Ctx &c, int lane)
+{
+    for (int r = 0; r < c.rounds; r++) {
+        const int item = lane + 32 * r;
+        const int4 d = c.mi[item];                                     // {first bin, stride, unused, unused}
+        const float4 w0 = *reinterpret_cast<const float4 *>(c.mw + item * W8_MEL_J);
+        const float4 w1 = *reinterpret_cast<const float4 *>(c.mw + item * W8_MEL_J + 4);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < W8_MEL_J; j++) {
+            int k = d.x + d.y * j;
+            k = k < 512 ? k : 512;                                     // padded entries carry weight 0
+            acc = fma2(c.pbuf[k], bc2(w[j]), acc);
+        }
+        c.part[item] = acc;
+    }
+}
+
+// ---- phase F: finish filter sums, floor, log, store log-mel ----------------------------------------
+DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
+{
+    for (int f = lane; f < c.n_mels; f += 32) {
+        const int2 d = c.filt[f];                                      // {first item, number of parts}
+        float2 s = make_float2(0.f, 0.f);
+        for (int i = 0; i < d.y; i++) s = add2(s, c.part[d.x + i]);
+        const float2 v = make_float2(logf(fmaxf(s.x, 1e-10f)), logf(fmaxf(s.y, 1e-10f)));
+        c.lm[f] = v;
+        if (c.logmelA) {
+            c.logmelA[f] = v.x;
+            if (c.validB) c.logmelB[f] = v.y;
+        }
+    }
+}
+
+// ---- phase G: DCT-II (table carries the factor 2), store MFCC -----------------------------------------
+DSPX_HD void w8_dct(const W8Ctx &c, int lane)
+{
+    if (!c.mfccA) return;
+    for (int q = lane; q < c.n_mfcc; q += 32) {
+        const float *basis = c.dct2 + q * c.n_mels;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int f = 0; f < c.n_mels; f++) acc = fma2(c.lm[f], bc2(basis[f]), acc);
+        c.mfccA[q] = acc.x;
+        if (c.validB) c.mfccB[q] = acc.y;
+    }
+}
+
+// set the per-item fields of the context (item = clip * pairs_per_clip + pair)
+DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, int64_t item)
+{
+    const int64_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
+    const int64_t tA = 2 * pair, tB = tA + 1;
+    c.validB = tB < p.n_frames;
+    c.clip = p.clips + clip * p.clip_stride;
+    c.sA = tA * p.hop;
+    c.sB = c.validB ? tB * p.hop : c.sA;
+    const int64_t rowA = clip * p.n_frames + tA, rowB = rowA + 1;
+    c.logmelA = p.logmel ? p.logmel + rowA * p.n_mels : nullptr;
+    c.logmelB = p.logmel ? p.logmel + rowB * p.n_mels : nullptr;
+    c.mfccA = p.mfcc ? p.mfcc + rowA * p.n_mfcc : nullptr;
+    c.mfccB = p.mfcc ? p.mfcc + rowB * p.n_mfcc : nullptr;
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(W8_WARPS * 32, 2) feat_warp8_kernel(const W8Params p)
+{
+    extern __shared__ __align__(16) float w8_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // constant tables: global -> shared, once per CTA
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.tables);
+        float4 *dst = reinterpret_cast<float4 *>(w8_smem);
+        for (int i = tid; i < p.tb.total / 4; i += W8_WARPS * 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    W8Ctx c;
+    w8_carve(w8_smem, w8_smem + p.tb.total + warp * w8_warp_floats(p.tb, p.n_mels), p.tb, c);
+    c.alpha = p.alpha;
+    c.pre = p.pre;
+    c.n_mels = p.n_mels;
+    c.n_mfcc = p.n_mfcc;
+    c.rounds = p.tb.rounds;
+    const int64_t n_warps = (int64_t)gridDim.x * W8_WARPS;
+    for (int64_t item = (int64_t)blockIdx.x * W8_WARPS + warp; item < p.n_items; item += n_warps) {
+        w8_set_item(p, c, item);
+        w8_pass1(c, lane);
+        __syncwarp();
+        w8_pass2(c, lane);
+        __syncwarp();
+        W8Power pw;
+        w8_pass3(c, lane, pw);
+        __syncwarp();                       // every lane has read its inputs: the tile may become P[]
+        w8_store_power(c, lane, pw);
+        __syncwarp();
+        w8_mel_items(c, lane);
+        __syncwarp();
+        w8_logmel(c, lane);
+        __syncwarp();
+        w8_dct(c, lane);
+        __syncwarp();
+    }
+}
+#endif
+
+// ---- host side: table blob, support check, launch -------------------------------------------------
+inline bool warp8_supported(const dspx_plan *pl)
+{
+    return pl->P == 1024 && pl->cfg.frame_length == 1024 && (pl->cfg.hop_length % 2) == 0 &&
+           pl->cfg.n_mels <= 256 && pl->cfg.n_mfcc <= 128;
+}
+
+inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8Tables &tb)
+{
+    const HostTables &h = pl->host;
+    const int n_mels = pl->cfg.n_mels, n_mfcc = pl->cfg.n_mfcc;
+    // mel work items: filter f with cnt bins -> ceil(cnt/8) items; item i reads bins start+i+parts*j
+    std::vector<int> first(n_mels), parts(n_mels);
+    int n_items = 0;
+    for (int f = 0; f < n_mels; f++) {
+        first[f] = n_items;
+        parts[f] = (h.fb_cnt[f] + W8_MEL_J - 1) / W8_MEL_J;
+        n_items += parts[f];
+    }
+    tb.rounds = std::max(1, (n_items + 31) / 32);
+    tb.n_slots = tb.rounds * 32;
+    auto al4 = [](int x) { return (x + 3) & ~3; };
+    int off = 0;
+    tb.win = off; off += 2 * 8 * 32 * 2;
+    tb.tw1 = off; off += 2 * 7 * 32 * 2;
+    tb.tw2 = off; off += al4(7 * 8 * 2);
+    tb.ptw = off; off += 9 * 32 * 2;
+    tb.mi = off; off += tb.n_slots * 4;
+    tb.mw = off; off += tb.n_slots * W8_MEL_J;
+    tb.filt = off; off += al4(n_mels * 2);
+    tb.dct2 = off; off += al4(n_mfcc * n_mels);
+    tb.total = al4(off);
+    blob.assign(tb.total, 0.f);
+    const double two_pi = 2.0 * M_PI;
+    for (int s = 0; s < 2; s++)
+        for (int a = 0; a < 8; a++)
+            for (int l = 0; l < 32; l++) {
+                const int n = 128 * a + 2 * (l + 32 * s);
+                blob[tb.win + ((s * 8 + a) * 32 + l) * 2] = (float)(0.5 * h.window[n]);
+                blob[tb.win + ((s * 8 + a) * 32 + l) * 2 + 1] = (float)(0.5 * h.window[n + 1]);
+            }
+    for (int s = 0; s < 2; s++)
+        for (int ka = 1; ka < 8; ka++)
+            for (int l = 0; l < 32; l++) {
+                const double ang = -two_pi * (double)((l + 32 * s) * ka) / 512.0;
+                blob[tb.tw1 + ((s * 7 + ka - 1) * 32 + l) * 2] = (float)std::cos(ang);
+                blob[tb.tw1 + ((s * 7 + ka - 1) * 32 + l) * 2 + 1] = (float)std::sin(ang);
+            }
+    for (int kb = 1; kb < 8; kb++)
+        for (int c = 0; c < 8; c++) {
+            const double ang = -two_pi * (double)(c * kb) / 64.0;
+            blob[tb.tw2 + ((kb - 1) * 8 + c) * 2] = (float)std::cos(ang);
+            blob[tb.tw2 + ((kb - 1) * 8 + c) * 2 + 1] = (float)std::sin(ang);
+        }
+    for (int m = 0; m < 9; m++)
+        for (int l = 0; l < 32; l++) {
+            const double ang = -two_pi * (double)w8_bin(l, m) / 1024.0;
+            blob[tb.ptw + (m * 32 + l) * 2] = (float)std::cos(ang);
+            blob[tb.ptw + (m * 32 + l) * 2 + 1] = (float)std::sin(ang);
+        }
+    int32_t *mi = reinterpret_cast<int32_t *>(blob.data() + tb.mi);
+    int32_t *filt = reinterpret_cast<int32_t *>(blob.data() + tb.filt);
+    for (int f = 0; f < n_mels; f++) {
+        filt[2 * f] = first[f];
+        filt[2 * f + 1] = parts[f];
+        for (int i = 0; i < parts[f]; i++) {
+            const int item = first[f] + i;
+            mi[4 * item] = h.fb_start[f] + i;
+            mi[4 * item + 1] = parts[f];
+            for (int j = 0; j < W8_MEL_J; j++) {
+                const int q = i + parts[f] * j;
+                blob[tb.mw + item * W8_MEL_J + j] = q < h.fb_cnt[f] ? h.fb_w[h.fb_off[f] + q] : 0.f;
+            }
+        }
+    }
+    for (int i = 0; i < n_mfcc * n_mels; i++) blob[tb.dct2 + i] = (float)h.dct2[i];
+}
+
+inline size_t warp8_smem_bytes(const W8Tables &tb, int n_mels)
+{
+    return ((size_t)tb.total + (size_t)W8_WARPS * w8_warp_floats(tb, n_mels)) * sizeof(float);
+}
+
+#if defined(__CUDACC__)
+struct W8PlanData {
+    W8Tables tb;
+    int ctas_per_sm;
+};
+
+inline int warp8_prepare(dspx_plan *pl)
+{
+    std::vector<float> blob;
+    W8Tables tb{};
+    warp8_build_tables(pl, blob, tb);
+    const size_t smem = warp8_smem_bytes(tb, pl->cfg.n_mels);
+    if (smem > 227 * 1024) { set_error("warp8: tables too large for shared memory"); return DSPX_EUNSUPPORTED; }
+    // header (W8PlanData) is kept on the host inside the plan; the blob goes to the device
+    auto *pd = new W8PlanData();
+    pd->tb = tb;
+    pd->ctas_per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+    DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));
+    DSPX_CUDA_CHECK(cudaMemcpy(pl->d_fast_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    pl->fast_tables_bytes = blob.size() * sizeof(float);
+    pl->fast_host = pd;
+    DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return DSPX_OK;
+}
+
+inline void warp8_release(dspx_plan *pl)
+{
+    delete static_cast<W8PlanData *>(pl->fast_host);
+    pl->fast_host = nullptr;
+}
+
+int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
+                            int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st);
+
+inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
+                        int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st)
+{
+    // 8-byte vector loads need even row strides and an 8-byte aligned base
+    if ((clip_stride & 1) || (reinterpret_cast<uintptr_t>(clips) & 7))
+        return launch_generic_fallback(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st);
+    const W8PlanData *pd = static_cast<const W8PlanData *>(pl->fast_host);
+    W8Params p{};
+    p.clips = clips;
+    p.n_clips = n_clips;
+    p.clip_stride = clip_stride;
+    p.n_frames = T;
+    p.pairs_per_clip = (T + 1) / 2;
+    p.n_items = n_clips * p.pairs_per_clip;
+    p.hop = pl->cfg.hop_length;
+    p.pre = pl->cfg.pre_emphasis > 0.0 ? 1 : 0;
+    p.n_mels = pl->cfg.n_mels;
+    p.n_mfcc = pl->cfg.n_mfcc;
+    p.alpha = (float)pl->cfg.pre_emphasis;
+    p.tb = pd->tb;
+    p.tables = static_cast<const float *>(pl->d_fast_tables);
+    p.logmel = logmel;
+    p.mfcc = mfcc;
+    const size_t smem = warp8_smem_bytes(pd->tb, p.n_mels);
+    int64_t ctas = (p.n_items + W8_WARPS - 1) / W8_WARPS;
+    const int64_t resident = (int64_t)pl->sm_count * pd->ctas_per_sm;
+    if (ctas > resident) ctas = resident;                    // persistent: warps stride over the items
+    feat_warp8_kernel<<<(unsigned)ctas, W8_WARPS * 32, smem, st>>>(p);
+    DSPX_CUDA_CHECK(cudaGetLastError());
+    return DSPX_OK;
+}
+#endif
+
 }  // namespace dspx

@@ -144,3 +144,42 @@ def test_generic_kernel_replay_matches_reference(built, golden_small):
             assert rel_err(mf[b], z[f"c{ci}_mfcc_{b}"]) < 1e-5, (ci, b)
             assert rel_err(lm[b], z[f"c{ci}_logmel_{b}"]) < 1e-5, (ci, b)
         assert rel_err(st[0, ..., 0] + 1j * st[0, ..., 1], z[f"c{ci}_stft_0"]) < 1e-6, ci
+
+
+def test_warp8_kernel_replay_matches_reference(built, golden_small):
+    """feat_warp8.cuh lane-phase functions (radix-8 f32x2 kernel) replayed on the CPU."""
+    lib, DspxConfig = _emu(built)
+    z, meta = golden_small
+    clips = np.ascontiguousarray(z["clips"])
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    covered = 0
+    for ci, m in enumerate(meta):
+        cfg = _cfg_struct(DspxConfig, m, kernel=2)
+        t = z[f"c{ci}_mfcc_0"].shape[0]
+        lm = np.zeros((3, t, m["n_mels"]), np.float32)
+        mf = np.zeros((3, t, m["n_mfcc"]), np.float32)
+        rc = lib.emu_features_warp8(C.byref(cfg), fp(clips), C.c_int64(3), C.c_int64(clips.shape[1]),
+                                    C.c_int64(clips.shape[1]), fp(lm), fp(mf))
+        supported = m["frame_length"] == 1024 and (m["n_fft"] in (None, 1024))
+        assert (rc == 0) == supported, (ci, rc)
+        if rc != 0:
+            continue
+        covered += 1
+        for b in range(3):
+            assert rel_err(mf[b], z[f"c{ci}_mfcc_{b}"]) < 1e-5, (ci, b)
+            assert rel_err(lm[b], z[f"c{ci}_logmel_{b}"]) < 1e-5, (ci, b)
+    assert covered >= 8
+
+
+def test_warp8_replay_full_clip(built, golden_config1):
+    lib, DspxConfig = _emu(built)
+    g = golden_config1
+    x = np.ascontiguousarray(g["clip"][None, :])
+    m = dict(sample_rate=44100, frame_length=1024, hop_length=512, n_fft=None, n_mels=40, n_mfcc=13, f_min=0.0,
+             f_max=None, pre_emphasis=0.97, window="hann")
+    cfg = _cfg_struct(DspxConfig, m, kernel=2)
+    lm = np.zeros((1, 429, 40), np.float32)
+    mf = np.zeros((1, 429, 13), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    assert lib.emu_features_warp8(C.byref(cfg), fp(x), C.c_int64(1), C.c_int64(220500), C.c_int64(220500), fp(lm), fp(mf)) == 0
+    assert rel_err(mf[0], g["mfcc"]) < 1e-5 and rel_err(lm[0], g["logmel"]) < 1e-5
