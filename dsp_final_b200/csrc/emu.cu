@@ -161,10 +161,9 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     p.n_clips = n_clips;
     p.clip_stride = clip_stride;
     p.n_frames = T;
-    p.pairs_per_clip = (T + 1) / 2;
-    p.n_items = n_clips * p.pairs_per_clip;
+    p.pairs_per_clip = (uint32_t)((T + 1) / 2);
+    p.n_items = (uint32_t)(n_clips * p.pairs_per_clip);
     p.hop = cfg->hop_length;
-    p.pre = cfg->pre_emphasis > 0.0 ? 1 : 0;
     p.n_mels = cfg->n_mels;
     p.n_mfcc = cfg->n_mfcc;
     p.alpha = (float)cfg->pre_emphasis;
@@ -172,27 +171,36 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     p.tables = blob.data();
     p.logmel = logmel;
     p.mfcc = mfcc;
+    const bool pre = cfg->pre_emphasis > 0.0;
     std::vector<float> warp_smem(w8_warp_floats(tb, p.n_mels) + 4, 0.f);
     W8Ctx c;
     // 16-byte align the warp tile like the device carve-up does
     float *ws = warp_smem.data();
     while (reinterpret_cast<uintptr_t>(ws) & 15) ws++;
-    w8_carve(blob.data(), ws, tb, c);
+    w8_carve(blob.data(), ws, tb, p.n_mels, c);
     c.alpha = p.alpha;
-    c.pre = p.pre;
     c.n_mels = p.n_mels;
     c.n_mfcc = p.n_mfcc;
     c.rounds = tb.rounds;
+    c.cw_lanes = tb.cw_lanes;
     std::vector<W8Power> pw(32);
-    for (int64_t item = 0; item < p.n_items; item++) {
+    for (uint32_t item = 0; item < p.n_items; item++) {
         w8_set_item(p, c, item);
-        for (int lane = 0; lane < 32; lane++) w8_pass1(c, lane);
+        for (int lane = 0; lane < 32; lane++) {
+            if (pre) w8_pass1<true>(c, lane);
+            else w8_pass1<false>(c, lane);
+        }
         for (int lane = 0; lane < 32; lane++) w8_pass2(c, lane);
         for (int lane = 0; lane < 32; lane++) w8_pass3(c, lane, pw[lane]);
         for (int lane = 0; lane < 32; lane++) w8_store_power(c, lane, pw[lane]);
-        for (int lane = 0; lane < 32; lane++) w8_mel_items(c, lane);
+        for (int lane = 0; lane < 32; lane++) w8_mel_chunks(c, lane);
         for (int lane = 0; lane < 32; lane++) w8_logmel(c, lane);
-        for (int lane = 0; lane < 32; lane++) w8_dct(c, lane);
+        if (c.mfccA) {
+            for (int c0 = 0; c0 < c.n_mfcc; c0 += c.cw_lanes) {
+                for (int lane = 0; lane < 32; lane++) w8_dct_partial(c, lane, c0);
+                for (int lane = 0; lane < 32; lane++) w8_dct_store(c, lane, c0);
+            }
+        }
     }
     return DSPX_OK;
 }

@@ -33,8 +33,8 @@
 namespace dspx {
 
 constexpr int W8_WARPS = 8;               // warps per CTA
-constexpr int W8_XFLOATS = 2048 + 16;     // per-warp exchange tile: 512 x (reA,reB,imA,imB); reused for P[513]
-constexpr int W8_MEL_J = 8;               // bins per mel work item
+
+
 
 // ---- packed two-frame arithmetic (x = frame A, y = frame B) ------------------------------
 #if defined(__CUDA_ARCH__)
@@ -107,15 +107,22 @@ DSPX_HD void dft8(float2 (&re)[8], float2 (&im)[8])
 // exchange-tile address (in float4 units) of element (k_a, x, c): x = b before pass 2, k_b after
 DSPX_HD int w8_addr(int ka, int x, int c) { return ((ka * 8 + x) << 3) | (c ^ ka); }
 
+constexpr int W8_CHUNK = 8;               // bins per mel chunk
+constexpr int W8_CSTRIDE = 10;            // float2 slots per chunk in the power tile (80 B: conflict-free LDS.128)
+constexpr int W8_WROW = 20;               // floats per chunk row of the weight table (a0 b0 .. a7 b7 + pad)
+
 struct W8Tables {            // offsets (in floats) into the packed table blob / shared memory
-    int win, tw1, tw2, ptw, mi, mw, filt, dct2, total;
-    int n_slots, rounds;
+    int win, tw1, tw2, ptw, ppos, cw, cflag, fdesc, dct, total;
+    int rounds, n_slots;     // mel chunks: 32 lanes x rounds (rounds odd)
+    int cw_lanes;            // DCT: coefficient lanes per part (16 or 32)
+    int tile_floats;         // per-warp exchange / power tile
 };
 
 struct W8Params {
     const float *clips;
-    int64_t n_clips, clip_stride, n_frames, pairs_per_clip, n_items;
-    int hop, pre, n_mels, n_mfcc;
+    int64_t n_clips, clip_stride, n_frames;
+    uint32_t pairs_per_clip, n_items;
+    int hop, n_mels, n_mfcc, prefetch;
     float alpha;
     W8Tables tb;
     const float *tables;     // global copy of the blob
@@ -124,16 +131,17 @@ struct W8Params {
 
 struct W8Ctx {               // everything one warp needs for one frame pair
     const float2 *win, *tw1, *tw2, *ptw;
-    const int4 *mi;
-    const float *mw;
-    const int2 *filt;
-    const float *dct2;
+    const int2 *ppos;
+    const float *cw;
+    const int *cflag;
+    const int4 *fdesc;
+    const float *dct;
     float4 *xbuf;
-    float2 *pbuf, *part, *lm;
-    const float *clip;       // first sample of the clip
-    int64_t sA, sB;          // first sample of frame A / B inside the clip
+    float2 *pbuf, *seg_a, *seg_b, *lm, *dsc;
+    const float *fa, *fb;    // first sample of frame A / frame B
+    int firstA, firstB;      // frame starts at sample 0 of its clip (no predecessor for pre-emphasis)
     float alpha;
-    int pre, n_mels, n_mfcc, rounds, validB;
+    int n_mels, n_mfcc, rounds, cw_lanes, validB;
     float *logmelA, *logmelB, *mfccA, *mfccB;   // rows of the two frames (null when not requested)
 };
 
@@ -141,43 +149,67 @@ struct W8Power {             // |X|^2 of the bins one lane owns, carried across 
     float2 lo[9], hi[9];
 };
 
-DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, W8Ctx &c)
+DSPX_HD int w8_warp_floats(const W8Tables &tb, int n_mels)
+{
+    return (tb.tile_floats + 4 * tb.n_slots + 2 * n_mels + 64 + 3) & ~3;
+}
+
+DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, int n_mels, W8Ctx &c)
 {
     c.win = reinterpret_cast<const float2 *>(tables_smem + tb.win);
     c.tw1 = reinterpret_cast<const float2 *>(tables_smem + tb.tw1);
     c.tw2 = reinterpret_cast<const float2 *>(tables_smem + tb.tw2);
     c.ptw = reinterpret_cast<const float2 *>(tables_smem + tb.ptw);
-    c.mi = reinterpret_cast<const int4 *>(tables_smem + tb.mi);
-    c.mw = tables_smem + tb.mw;
-    c.filt = reinterpret_cast<const int2 *>(tables_smem + tb.filt);
-    c.dct2 = tables_smem + tb.dct2;
+    c.ppos = reinterpret_cast<const int2 *>(tables_smem + tb.ppos);
+    c.cw = tables_smem + tb.cw;
+    c.cflag = reinterpret_cast<const int *>(tables_smem + tb.cflag);
+    c.fdesc = reinterpret_cast<const int4 *>(tables_smem + tb.fdesc);
+    c.dct = tables_smem + tb.dct;
     c.xbuf = reinterpret_cast<float4 *>(warp_smem);
     c.pbuf = reinterpret_cast<float2 *>(warp_smem);
-    c.part = reinterpret_cast<float2 *>(warp_smem + W8_XFLOATS);
-    c.lm = c.part + tb.n_slots;
+    c.seg_a = reinterpret_cast<float2 *>(warp_smem + tb.tile_floats);
+    c.seg_b = c.seg_a + tb.n_slots;
+    c.lm = c.seg_b + tb.n_slots;
+    c.dsc = c.lm + n_mels;
 }
 
-DSPX_HD int w8_warp_floats(const W8Tables &tb, int n_mels) { return (W8_XFLOATS + 2 * tb.n_slots + 2 * n_mels + 3) & ~3; }
-
 // ---- phase A: load, pre-emphasis, window, radix-8 over a, twiddle, store -----------------
+// All 32 loads of a set are issued before the first use (memory-level parallelism); the only
+// sample without a predecessor is sample 0 of a clip (y[0] = x[0], src/dsp/mfcc.py:88).
+template <bool PRE>
 DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 {
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         const int tid = lane + 32 * s;
+        const float *pa = c.fa + 2 * tid, *pb = c.fb + 2 * tid;
+        float2 xa[8], xb[8];
+        float pva[8], pvb[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            xa[a] = *reinterpret_cast<const float2 *>(pa + 128 * a);
+            xb[a] = *reinterpret_cast<const float2 *>(pb + 128 * a);
+        }
+        if (PRE) {
+            const bool edgeA = c.firstA && tid == 0, edgeB = c.firstB && tid == 0;
+            pva[0] = *(edgeA ? pa : pa - 1);
+            pvb[0] = *(edgeB ? pb : pb - 1);
+            if (edgeA) pva[0] = 0.f;
+            if (edgeB) pvb[0] = 0.f;
+#pragma unroll
+            for (int a = 1; a < 8; a++) {
+                pva[a] = pa[128 * a - 1];
+                pvb[a] = pb[128 * a - 1];
+            }
+        }
         float2 re[8], im[8];
 #pragma unroll
         for (int a = 0; a < 8; a++) {
-            const int n = 128 * a + 2 * tid;
-            const float *pa = c.clip + c.sA + n, *pb = c.clip + c.sB + n;
-            const float2 xa = *reinterpret_cast<const float2 *>(pa);
-            const float2 xb = *reinterpret_cast<const float2 *>(pb);
-            float2 y0 = make_float2(xa.x, xb.x), y1 = make_float2(xa.y, xb.y);
-            if (c.pre) {
-                const float2 pv = make_float2(c.sA + n > 0 ? pa[-1] : 0.f, c.sB + n > 0 ? pb[-1] : 0.f);
+            float2 y0 = make_float2(xa[a].x, xb[a].x), y1 = make_float2(xa[a].y, xb[a].y);
+            if (PRE) {
                 const float2 al = bc2(c.alpha);
-                const float2 t0 = mul2(pv, al), t1 = mul2(y0, al);      // rounded products ...
-                y1 = sub2(y1, t1);                                      // ... then rounded differences
+                const float2 t0 = mul2(make_float2(pva[a], pvb[a]), al), t1 = mul2(y0, al);   // rounded products ...
+                y1 = sub2(y1, t1);                                                          // ... rounded differences
                 y0 = sub2(y0, t0);
             }
             const float2 w = c.win[(s * 8 + a) * 32 + lane];            // (0.5 w[n], 0.5 w[n+1])
@@ -276,46 +308,74 @@ DSPX_HD int w8_bin(int lane, int m)      // bin index of slot m
     return lane == 0 ? k0[m] : lane + 64 * m;
 }
 
-// ---- phase D: power spectrum to the (re-used) tile, natural bin order ---------------------------
+// ---- phase D: power spectrum into the (re-used) tile, in mel-chunk order ---------------------------
+// ppos[m][lane] = tile slots of bins k_m and 512 - k_m: bins of one mel chunk are contiguous,
+// chunks sit W8_CSTRIDE slots apart, bins no filter uses go to a dump slot.
 DSPX_HD void w8_store_power(const W8Ctx &c, int lane, const W8Power &pw)
 {
 #pragma unroll
     for (int m = 0; m < 8; m++) {
-        const int k = w8_bin(lane, m);
-        c.pbuf[k] = pw.lo[m];
-        c.pbuf[512 - k] = pw.hi[m];
+        const int2 p = c.ppos[m * 32 + lane];
+        c.pbuf[p.x] = pw.lo[m];
+        c.pbuf[p.y] = pw.hi[m];
     }
-    if (lane == 0) { c.pbuf[224] = pw.lo[8]; c.pbuf[288] = pw.hi[8]; }
+    if (lane == 0) {
+        const int2 p = c.ppos[8 * 32];
+        c.pbuf[p.x] = pw.lo[8];
+        c.pbuf[p.y] = pw.hi[8];
+    }
 }
 
-// ---- phase E: mel work items: 8 strided bins of one filter each ----------------------------------
-DSPX_HD void w8_mel_items(const W8Ctx &c, int lane)
+// ---- phase E: mel chunks ----------------------------------------------------------------------------
+// Every bin k feeds (at most) filter g(k) with weight a_k and filter g(k)+1 with weight b_k
+// (csrc/tables.cuh "bin view").  Runs of equal g are cut into chunks of 8 bins; lane l walks
+// chunks l*R .. l*R+R-1, accumulating in registers while the run continues and dropping one
+// (sum a P, sum b P) segment per run piece.  P and weight rows are 80 bytes apart: the
+// 128-bit loads of 8 neighbouring lanes hit 8 different bank groups.
+DSPX_HD void w8_mel_chunks(const W8Ctx &c, int lane)
 {
+    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
     for (int r = 0; r < c.rounds; r++) {
-        const int item = lane + 32 * r;
-        const int4 d = c.mi[item];                                     // {first bin, stride, unused, unused}
-        const float4 w0 = *reinterpret_cast<const float4 *>(c.mw + item * W8_MEL_J);
-        const float4 w1 = *reinterpret_cast<const float4 *>(c.mw + item * W8_MEL_J + 4);
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        float2 acc = make_float2(0.f, 0.f);
+        const int ch = lane * c.rounds + r;
+        const int flag = c.cflag[ch];                                   // bit0 first, bit1 last, >>8 segment
+        const float4 *pp = reinterpret_cast<const float4 *>(c.pbuf + ch * W8_CSTRIDE);
+        const float4 *ww = reinterpret_cast<const float4 *>(c.cw + ch * W8_WROW);
+        float2 ca = make_float2(0.f, 0.f), cb = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < W8_MEL_J; j++) {
-            int k = d.x + d.y * j;
-            k = k < 512 ? k : 512;                                     // padded entries carry weight 0
-            acc = fma2(c.pbuf[k], bc2(w[j]), acc);
+        for (int q = 0; q < 4; q++) {
+            const float4 p = pp[q], w = ww[q];                          // (P0A P0B P1A P1B), (a0 b0 a1 b1)
+            ca = fma2(make_float2(p.x, p.y), bc2(w.x), ca);
+            cb = fma2(make_float2(p.x, p.y), bc2(w.y), cb);
+            ca = fma2(make_float2(p.z, p.w), bc2(w.z), ca);
+            cb = fma2(make_float2(p.z, p.w), bc2(w.w), cb);
         }
-        c.part[item] = acc;
+        if (flag & 1) { sa = ca; sb = cb; }
+        else { sa = add2(sa, ca); sb = add2(sb, cb); }
+        if (flag & 2) {
+            c.seg_a[flag >> 8] = sa;
+            c.seg_b[flag >> 8] = sb;
+        }
     }
 }
 
-// ---- phase F: finish filter sums, floor, log, store log-mel ----------------------------------------
+// ---- phase F: filter sums from the segments, floor, log, store log-mel ---------------------------------
+DSPX_HD float w8_log(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __logf(x);        // lg2.approx * ln 2: abs err < 1e-6 on values of magnitude 1..25 (tolerance 1e-4)
+#else
+    return logf(x);
+#endif
+}
+
 DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
 {
     for (int f = lane; f < c.n_mels; f += 32) {
-        const int2 d = c.filt[f];                                      // {first item, number of parts}
+        const int4 d = c.fdesc[f];                                     // {a first, a count, b first, b count}
         float2 s = make_float2(0.f, 0.f);
-        for (int i = 0; i < d.y; i++) s = add2(s, c.part[d.x + i]);
-        const float2 v = make_float2(logf(fmaxf(s.x, 1e-10f)), logf(fmaxf(s.y, 1e-10f)));
+        for (int i = 0; i < d.y; i++) s = add2(s, c.seg_a[d.x + i]);
+        for (int i = 0; i < d.w; i++) s = add2(s, c.seg_b[d.z + i]);
+        const float2 v = make_float2(w8_log(fmaxf(s.x, 1e-10f)), w8_log(fmaxf(s.y, 1e-10f)));
         c.lm[f] = v;
         if (c.logmelA) {
             c.logmelA[f] = v.x;
@@ -324,29 +384,45 @@ DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
     }
 }
 
-// ---- phase G: DCT-II (table carries the factor 2), store MFCC -----------------------------------------
-DSPX_HD void w8_dct(const W8Ctx &c, int lane)
+// ---- phase G/H: DCT-II (table carries the factor 2) in cw_lanes-wide coefficient blocks ---------------
+// lane = part * cw_lanes + q: part p sums filters p, p + parts, ...; table row f is cw_lanes wide,
+// so a warp load touches one row per part: conflict-free.  Parts are combined through dsc[].
+DSPX_HD void w8_dct_partial(const W8Ctx &c, int lane, int c0)
 {
-    if (!c.mfccA) return;
-    for (int q = lane; q < c.n_mfcc; q += 32) {
-        const float *basis = c.dct2 + q * c.n_mels;
-        float2 acc = make_float2(0.f, 0.f);
-        for (int f = 0; f < c.n_mels; f++) acc = fma2(c.lm[f], bc2(basis[f]), acc);
-        c.mfccA[q] = acc.x;
-        if (c.validB) c.mfccB[q] = acc.y;
+    const int cwl = c.cw_lanes, parts = 32 / cwl;
+    const int q = lane & (cwl - 1), part = lane / cwl;
+    const int blocks = (c.n_mfcc + cwl - 1) / cwl;
+    const float *col = c.dct + (size_t)(c0 / cwl) * c.n_mels * cwl + q;     // block-major table
+    (void)blocks;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int f = part; f < c.n_mels; f += parts) acc = fma2(c.lm[f], bc2(col[f * cwl]), acc);
+    c.dsc[lane] = acc;
+}
+
+DSPX_HD void w8_dct_store(const W8Ctx &c, int lane, int c0)
+{
+    const int cwl = c.cw_lanes;
+    const int q = c0 + lane;
+    if (lane < cwl && q < c.n_mfcc) {
+        float2 v = c.dsc[lane];
+        if (cwl == 16) v = add2(v, c.dsc[lane + 16]);
+        c.mfccA[q] = v.x;
+        if (c.validB) c.mfccB[q] = v.y;
     }
 }
 
 // set the per-item fields of the context (item = clip * pairs_per_clip + pair)
-DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, int64_t item)
+DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
 {
-    const int64_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
-    const int64_t tA = 2 * pair, tB = tA + 1;
+    const uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
+    const int64_t tA = 2 * (int64_t)pair, tB = tA + 1;
     c.validB = tB < p.n_frames;
-    c.clip = p.clips + clip * p.clip_stride;
-    c.sA = tA * p.hop;
-    c.sB = c.validB ? tB * p.hop : c.sA;
-    const int64_t rowA = clip * p.n_frames + tA, rowB = rowA + 1;
+    const float *base = p.clips + (int64_t)clip * p.clip_stride;
+    c.fa = base + tA * p.hop;
+    c.fb = c.validB ? base + tB * p.hop : c.fa;
+    c.firstA = pair == 0;
+    c.firstB = c.validB ? 0 : c.firstA;        // a missing frame B replays frame A
+    const int64_t rowA = (int64_t)clip * p.n_frames + tA, rowB = rowA + 1;
     c.logmelA = p.logmel ? p.logmel + rowA * p.n_mels : nullptr;
     c.logmelB = p.logmel ? p.logmel + rowB * p.n_mels : nullptr;
     c.mfccA = p.mfcc ? p.mfcc + rowA * p.n_mfcc : nullptr;
@@ -354,28 +430,45 @@ DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, int64_t item)
 }
 
 #if defined(__CUDACC__)
+// pull the next item's samples towards L2 while this one is being transformed
+__device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, int lane)
+{
+    if (item >= p.n_items) return;
+    const uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
+    const char *base = reinterpret_cast<const char *>(p.clips + (int64_t)clip * p.clip_stride + 2 * (int64_t)pair * p.hop);
+    const int span = (p.hop + 1024) * 4;                       // bytes covered by the frame pair
+    for (int off = lane * 128; off < span; off += 32 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
+template <bool PRE>
 __global__ void __launch_bounds__(W8_WARPS * 32, 2) feat_warp8_kernel(const W8Params p)
 {
     extern __shared__ __align__(16) float w8_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // constant tables: global -> shared, once per CTA
+    const int wf = w8_warp_floats(p.tb, p.n_mels);
+    // constant tables: global -> shared, once per CTA; zero the per-warp areas (pad slots of the
+    // power tile are read with zero weights and must hold finite numbers)
     {
         const float4 *src = reinterpret_cast<const float4 *>(p.tables);
         float4 *dst = reinterpret_cast<float4 *>(w8_smem);
         for (int i = tid; i < p.tb.total / 4; i += W8_WARPS * 32) dst[i] = src[i];
+        float4 *z = reinterpret_cast<float4 *>(w8_smem + p.tb.total);
+        for (int i = tid; i < W8_WARPS * wf / 4; i += W8_WARPS * 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     W8Ctx c;
-    w8_carve(w8_smem, w8_smem + p.tb.total + warp * w8_warp_floats(p.tb, p.n_mels), p.tb, c);
+    w8_carve(w8_smem, w8_smem + p.tb.total + warp * wf, p.tb, p.n_mels, c);
     c.alpha = p.alpha;
-    c.pre = p.pre;
     c.n_mels = p.n_mels;
     c.n_mfcc = p.n_mfcc;
     c.rounds = p.tb.rounds;
-    const int64_t n_warps = (int64_t)gridDim.x * W8_WARPS;
-    for (int64_t item = (int64_t)blockIdx.x * W8_WARPS + warp; item < p.n_items; item += n_warps) {
+    c.cw_lanes = p.tb.cw_lanes;
+    const uint32_t n_warps = gridDim.x * W8_WARPS;
+    for (uint32_t item = blockIdx.x * W8_WARPS + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
-        w8_pass1(c, lane);
+        w8_pass1<PRE>(c, lane);
+        if (p.prefetch) w8_prefetch(p, item + n_warps, lane);
         __syncwarp();
         w8_pass2(c, lane);
         __syncwarp();
@@ -384,12 +477,18 @@ __global__ void __launch_bounds__(W8_WARPS * 32, 2) feat_warp8_kernel(const W8Pa
         __syncwarp();                       // every lane has read its inputs: the tile may become P[]
         w8_store_power(c, lane, pw);
         __syncwarp();
-        w8_mel_items(c, lane);
+        w8_mel_chunks(c, lane);
         __syncwarp();
         w8_logmel(c, lane);
         __syncwarp();
-        w8_dct(c, lane);
-        __syncwarp();
+        if (c.mfccA) {
+            for (int c0 = 0; c0 < c.n_mfcc; c0 += c.cw_lanes) {
+                w8_dct_partial(c, lane, c0);
+                __syncwarp();
+                w8_dct_store(c, lane, c0);
+                __syncwarp();
+            }
+        }
     }
 }
 #endif
@@ -398,33 +497,46 @@ __global__ void __launch_bounds__(W8_WARPS * 32, 2) feat_warp8_kernel(const W8Pa
 inline bool warp8_supported(const dspx_plan *pl)
 {
     return pl->P == 1024 && pl->cfg.frame_length == 1024 && (pl->cfg.hop_length % 2) == 0 &&
-           pl->cfg.n_mels <= 256 && pl->cfg.n_mfcc <= 128;
+           pl->cfg.n_mels <= 256 && pl->cfg.n_mfcc <= 128 && pl->host.two_band_ok;
 }
 
 inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8Tables &tb)
 {
     const HostTables &h = pl->host;
-    const int n_mels = pl->cfg.n_mels, n_mfcc = pl->cfg.n_mfcc;
-    // mel work items: filter f with cnt bins -> ceil(cnt/8) items; item i reads bins start+i+parts*j
-    std::vector<int> first(n_mels), parts(n_mels);
-    int n_items = 0;
-    for (int f = 0; f < n_mels; f++) {
-        first[f] = n_items;
-        parts[f] = (h.fb_cnt[f] + W8_MEL_J - 1) / W8_MEL_J;
-        n_items += parts[f];
+    const int n_mels = pl->cfg.n_mels, n_mfcc = pl->cfg.n_mfcc, n_bins = 513;
+    // --- mel chunks from the bin view: runs of equal g, cut into chunks of 8 bins ---
+    struct Chunk { int run, start, count; };
+    std::vector<Chunk> chunks;
+    std::vector<int> run_g;
+    for (int k = 0; k < n_bins;) {
+        const int g = h.bin_filt[k];
+        if (g < 0) { k++; continue; }
+        int e = k;
+        while (e < n_bins && h.bin_filt[e] == g) e++;
+        const int run = (int)run_g.size();
+        run_g.push_back(g);
+        for (int s = k; s < e; s += W8_CHUNK) chunks.push_back({run, s, std::min(W8_CHUNK, e - s)});
+        k = e;
     }
-    tb.rounds = std::max(1, (n_items + 31) / 32);
-    tb.n_slots = tb.rounds * 32;
+    const int n_chunks = (int)chunks.size();
+    int rounds = std::max(1, (n_chunks + 31) / 32);
+    if (rounds % 2 == 0) rounds++;                       // odd: lanes' 80-byte rows stay conflict-free
+    tb.rounds = rounds;
+    tb.n_slots = 32 * rounds;
+    tb.cw_lanes = n_mfcc <= 16 ? 16 : 32;
+    const int dct_blocks = (n_mfcc + tb.cw_lanes - 1) / tb.cw_lanes;
+    tb.tile_floats = std::max(2048, 2 * (W8_CSTRIDE * tb.n_slots + 16)) + 16;
     auto al4 = [](int x) { return (x + 3) & ~3; };
     int off = 0;
     tb.win = off; off += 2 * 8 * 32 * 2;
     tb.tw1 = off; off += 2 * 7 * 32 * 2;
     tb.tw2 = off; off += al4(7 * 8 * 2);
     tb.ptw = off; off += 9 * 32 * 2;
-    tb.mi = off; off += tb.n_slots * 4;
-    tb.mw = off; off += tb.n_slots * W8_MEL_J;
-    tb.filt = off; off += al4(n_mels * 2);
-    tb.dct2 = off; off += al4(n_mfcc * n_mels);
+    tb.ppos = off; off += 9 * 32 * 2;
+    tb.cw = off; off += tb.n_slots * W8_WROW;
+    tb.cflag = off; off += tb.n_slots;
+    tb.fdesc = off; off += n_mels * 4;
+    tb.dct = off; off += al4(dct_blocks * n_mels * tb.cw_lanes);
     tb.total = al4(off);
     blob.assign(tb.total, 0.f);
     const double two_pi = 2.0 * M_PI;
@@ -454,22 +566,50 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
             blob[tb.ptw + (m * 32 + l) * 2] = (float)std::cos(ang);
             blob[tb.ptw + (m * 32 + l) * 2 + 1] = (float)std::sin(ang);
         }
-    int32_t *mi = reinterpret_cast<int32_t *>(blob.data() + tb.mi);
-    int32_t *filt = reinterpret_cast<int32_t *>(blob.data() + tb.filt);
-    for (int f = 0; f < n_mels; f++) {
-        filt[2 * f] = first[f];
-        filt[2 * f + 1] = parts[f];
-        for (int i = 0; i < parts[f]; i++) {
-            const int item = first[f] + i;
-            mi[4 * item] = h.fb_start[f] + i;
-            mi[4 * item + 1] = parts[f];
-            for (int j = 0; j < W8_MEL_J; j++) {
-                const int q = i + parts[f] * j;
-                blob[tb.mw + item * W8_MEL_J + j] = q < h.fb_cnt[f] ? h.fb_w[h.fb_off[f] + q] : 0.f;
-            }
+    // chunk c lives at (lane = c / rounds, round = c % rounds); its bins sit at tile slots 10c .. 10c+7
+    std::vector<int> pos(n_bins, W8_CSTRIDE * tb.n_slots + 8);          // dump slot for unused bins
+    int32_t *cflag = reinterpret_cast<int32_t *>(blob.data() + tb.cflag);
+    const int n_runs = (int)run_g.size();
+    std::vector<int> seg_first(n_runs, 0), seg_cnt(n_runs, 0);
+    int seg = 0;
+    for (int ci = 0; ci < n_chunks; ci++) {
+        const Chunk &ch = chunks[ci];
+        for (int j = 0; j < ch.count; j++) {
+            const int k = ch.start + j;
+            pos[k] = W8_CSTRIDE * ci + j;
+            blob[tb.cw + ci * W8_WROW + 2 * j] = h.bin_wfall[k];
+            blob[tb.cw + ci * W8_WROW + 2 * j + 1] = h.bin_wrise[k];
+        }
+        const bool first = (ci % rounds == 0) || chunks[ci - 1].run != ch.run;
+        const bool last = (ci % rounds == rounds - 1) || ci == n_chunks - 1 || chunks[ci + 1].run != ch.run;
+        if (first && seg_cnt[ch.run] == 0) seg_first[ch.run] = seg;
+        cflag[ci] = (first ? 1 : 0) | (last ? 2 : 0) | (seg << 8);
+        if (last) { seg_cnt[ch.run]++; seg++; }
+    }
+    int32_t *ppos = reinterpret_cast<int32_t *>(blob.data() + tb.ppos);
+    for (int m = 0; m < 9; m++)
+        for (int l = 0; l < 32; l++) {
+            const int k = w8_bin(l, m);
+            ppos[(m * 32 + l) * 2] = pos[k];
+            ppos[(m * 32 + l) * 2 + 1] = pos[512 - k];
+        }
+    int32_t *fdesc = reinterpret_cast<int32_t *>(blob.data() + tb.fdesc);
+    for (int r = 0; r < n_runs; r++) {
+        const int g = run_g[r];
+        fdesc[4 * g] = seg_first[r];                       // filter g collects the "a" sums of run g ...
+        fdesc[4 * g + 1] = seg_cnt[r];
+        if (g + 1 < n_mels) {                              // ... and filter g+1 the "b" sums
+            fdesc[4 * (g + 1) + 2] = seg_first[r];
+            fdesc[4 * (g + 1) + 3] = seg_cnt[r];
         }
     }
-    for (int i = 0; i < n_mfcc * n_mels; i++) blob[tb.dct2 + i] = (float)h.dct2[i];
+    // DCT table, block-major: [block][filter][cw_lanes], zero beyond n_mfcc
+    for (int b = 0; b < dct_blocks; b++)
+        for (int f = 0; f < n_mels; f++)
+            for (int q = 0; q < tb.cw_lanes; q++) {
+                const int cidx = b * tb.cw_lanes + q;
+                blob[tb.dct + (b * n_mels + f) * tb.cw_lanes + q] = cidx < n_mfcc ? (float)h.dct2[(size_t)cidx * n_mels + f] : 0.f;
+            }
 }
 
 inline size_t warp8_smem_bytes(const W8Tables &tb, int n_mels)
@@ -481,6 +621,7 @@ inline size_t warp8_smem_bytes(const W8Tables &tb, int n_mels)
 struct W8PlanData {
     W8Tables tb;
     int ctas_per_sm;
+    size_t smem;
 };
 
 inline int warp8_prepare(dspx_plan *pl)
@@ -490,15 +631,14 @@ inline int warp8_prepare(dspx_plan *pl)
     warp8_build_tables(pl, blob, tb);
     const size_t smem = warp8_smem_bytes(tb, pl->cfg.n_mels);
     if (smem > 227 * 1024) { set_error("warp8: tables too large for shared memory"); return DSPX_EUNSUPPORTED; }
-    // header (W8PlanData) is kept on the host inside the plan; the blob goes to the device
     auto *pd = new W8PlanData();
     pd->tb = tb;
+    pd->smem = smem;
     pd->ctas_per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+    pl->fast_host = pd;
     DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));
     DSPX_CUDA_CHECK(cudaMemcpy(pl->d_fast_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
     pl->fast_tables_bytes = blob.size() * sizeof(float);
-    pl->fast_host = pd;
-    DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return DSPX_OK;
 }
 
@@ -514,8 +654,9 @@ int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_c
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                         int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st)
 {
-    // 8-byte vector loads need even row strides and an 8-byte aligned base
-    if ((clip_stride & 1) || (reinterpret_cast<uintptr_t>(clips) & 7))
+    const int64_t pairs = (T + 1) / 2;
+    // 8-byte vector loads need even row strides and an 8-byte aligned base; items are 32-bit
+    if ((clip_stride & 1) || (reinterpret_cast<uintptr_t>(clips) & 7) || n_clips * pairs >= (int64_t)0x7fffffff)
         return launch_generic_fallback(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st);
     const W8PlanData *pd = static_cast<const W8PlanData *>(pl->fast_host);
     W8Params p{};
@@ -523,22 +664,31 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.n_clips = n_clips;
     p.clip_stride = clip_stride;
     p.n_frames = T;
-    p.pairs_per_clip = (T + 1) / 2;
-    p.n_items = n_clips * p.pairs_per_clip;
+    p.pairs_per_clip = (uint32_t)pairs;
+    p.n_items = (uint32_t)(n_clips * pairs);
     p.hop = pl->cfg.hop_length;
-    p.pre = pl->cfg.pre_emphasis > 0.0 ? 1 : 0;
     p.n_mels = pl->cfg.n_mels;
     p.n_mfcc = pl->cfg.n_mfcc;
+    p.prefetch = 1;
     p.alpha = (float)pl->cfg.pre_emphasis;
     p.tb = pd->tb;
     p.tables = static_cast<const float *>(pl->d_fast_tables);
     p.logmel = logmel;
     p.mfcc = mfcc;
-    const size_t smem = warp8_smem_bytes(pd->tb, p.n_mels);
-    int64_t ctas = (p.n_items + W8_WARPS - 1) / W8_WARPS;
+    int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
     const int64_t resident = (int64_t)pl->sm_count * pd->ctas_per_sm;
     if (ctas > resident) ctas = resident;                    // persistent: warps stride over the items
-    feat_warp8_kernel<<<(unsigned)ctas, W8_WARPS * 32, smem, st>>>(p);
+    // the opt-in shared-memory limit is a per-function attribute shared by all plans: only ever raise it
+    static size_t smem_set_dev[64][2] = {};
+    const bool pre = pl->cfg.pre_emphasis > 0.0;
+    size_t *smem_set = smem_set_dev[pl->device & 63];
+    if (pd->smem > smem_set[pre]) {
+        if (pre) DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
+        else DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
+        smem_set[pre] = pd->smem;
+    }
+    if (pre) feat_warp8_kernel<true><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
+    else feat_warp8_kernel<false><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
 }
