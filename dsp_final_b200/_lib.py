@@ -20,7 +20,7 @@ WINDOWS = {"hann": 0, "hamming": 1, "rect": 2}
 KERNELS = {"auto": 0, "generic": 1, "warp8": 2}
 KERNEL_NAMES = {v: k for k, v in KERNELS.items()}
 DTYPE_F32, DTYPE_F64 = 0, 1
-MAX_K = 256
+MAX_K = 128
 
 
 class DspxConfig(C.Structure):

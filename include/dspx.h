@@ -145,7 +145,7 @@ int dspx_fft_c2c(const float *in_dev, int64_t batch, int64_t n_in, int64_t n, in
  * 1/(||row|| + 1e-10); idx_out [nq, k] int32 in descending score order, ties broken by
  * the lower database index (np.argsort(..., kind="stable")).  score_out may be NULL.
  * workspace_dev must hold dspx_cosine_topk_workspace() bytes.  k <= DSPX_MAX_K. */
-#define DSPX_MAX_K 256
+#define DSPX_MAX_K 128
 size_t dspx_cosine_topk_workspace(int64_t nq, int64_t ndb, int dim, int k);
 int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t ndb, int dim,
                      int dtype, int k, int32_t *idx_out_dev, double *score_out_dev,
