@@ -1,4 +1,6 @@
-"""Drop-in for the reference package src/dsp (same module and function names)."""
-from .fft import fft, ifft, rfft  # noqa: F401
-from .mfcc import MfccConfig, dct_type_2, log_mel_spectrogram, mel_filterbank, mfcc  # noqa: F401
-from .stft import WindowType, frame_signal, stft  # noqa: F401
+"""Drop-in for the reference package src/dsp: submodules fft, stft, mfcc with the same names.
+
+Like the reference's (empty) src/dsp/__init__.py this does not re-export the functions: `fft`,
+`stft` and `mfcc` are both submodule and function names, and re-exporting them would shadow the
+submodules for `import dsp_final_b200.dsp.mfcc as m`.
+"""

@@ -64,7 +64,8 @@ def test_golden_small_cases(torch_cuda, golden_small, kernel):
 
 def test_reference_signatures_config1(torch_cuda, golden_config1):
     """BASELINE.json configs[0]: one 5 s clip through the reference-named entry points."""
-    from dsp_final_b200.dsp import MfccConfig, log_mel_spectrogram, mfcc, stft
+    from dsp_final_b200.dsp.mfcc import MfccConfig, log_mel_spectrogram, mfcc
+    from dsp_final_b200.dsp.stft import stft
 
     g = golden_config1
     x = g["clip"]
@@ -82,7 +83,8 @@ def test_reference_signatures_config1(torch_cuda, golden_config1):
 
 
 def test_real_clip_excerpt(torch_cuda, golden_real):
-    from dsp_final_b200.dsp import MfccConfig, log_mel_spectrogram, mfcc, stft
+    from dsp_final_b200.dsp.mfcc import MfccConfig, log_mel_spectrogram, mfcc
+    from dsp_final_b200.dsp.stft import stft
 
     g = golden_real
     x = g["pcm16"].astype(np.float32) / np.float32(32768.0)
@@ -158,7 +160,7 @@ def test_host_pipeline_many_chunks(torch_cuda):
 
 
 def test_fft_family(torch_cuda, golden_fft):
-    from dsp_final_b200.dsp import fft, ifft, rfft
+    from dsp_final_b200.dsp.fft import fft, ifft, rfft
 
     g = golden_fft
     for i in range(int(g["n_cases"])):
@@ -179,7 +181,8 @@ def test_fft_family(torch_cuda, golden_fft):
 
 
 def test_errors_follow_the_reference(torch_cuda):
-    from dsp_final_b200.dsp import MfccConfig, mfcc, stft
+    from dsp_final_b200.dsp.mfcc import MfccConfig, mfcc
+    from dsp_final_b200.dsp.stft import stft
     from dsp_final_b200.dsp.stft import _get_window, frame_signal
 
     x = np.zeros(4000, np.float32)

@@ -89,7 +89,7 @@ def test_product_fails_loudly_without_a_gpu(built):
     if torch.cuda.is_available():
         pytest.skip("has a GPU")
     from dsp_final_b200 import _lib
-    from dsp_final_b200.dsp import MfccConfig, mfcc
+    from dsp_final_b200.dsp.mfcc import MfccConfig, mfcc
 
     with pytest.raises(_lib.DspxError):
         mfcc(np.zeros(4096, np.float32), MfccConfig(44100, 1024, 512))
