@@ -66,6 +66,14 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback"
 
 
+def host_cores() -> int:
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:                                    # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -124,7 +132,7 @@ def cpu_arm(args, n_frames: int):
     from oracle import oracle as O
 
     cfg = O.OracleConfig(SR, FL, HOP, n_mels=N_MELS, n_mfcc=N_MFCC)
-    cores = O.max_threads()
+    cores = host_cores()
     want = tuple(n for n in ("mfcc", "log_mel") if n in args.outputs)
     per_step = max(cores, 8)
     clips = synth.host_clips(min(per_step, 64), seed=1234)
@@ -141,7 +149,7 @@ def run_reference(args) -> None:
     O, cfg, cores, want, clips = cpu_arm(args, n_frames)
     per_step = clips.shape[0]
     t0 = time.perf_counter()
-    O.features_batch(clips, cfg, want=want)                       # calibration step (counts as warm-up)
+    O.features_batch(clips, cfg, want=want, n_threads=cores)                       # calibration step (counts as warm-up)
     one = time.perf_counter() - t0
     # keep the whole run within a few minutes whatever K is
     budget = 150.0
@@ -151,10 +159,10 @@ def run_reference(args) -> None:
         clips = clips[:shrink]
         per_step = clips.shape[0]
     for _ in range(warm):
-        O.features_batch(clips, cfg, want=want)
+        O.features_batch(clips, cfg, want=want, n_threads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.features_batch(clips, cfg, want=want)
+        O.features_batch(clips, cfg, want=want, n_threads=cores)
     dt = time.perf_counter() - t0
     value = per_step * CLIP_SECONDS * steps / dt
     sample = f"{per_step} synthetic 5 s clips per step x {steps} steps, C port of src/dsp (complex128 radix-2), OpenMP over clips"
@@ -303,16 +311,16 @@ def run_ours(args) -> None:
     parity["clips_checked"] = len(sel)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = O.max_threads()
+        cores = host_cores()
         host = synth.host_clips(min(max(cores, 8), 64), seed=1234)
         t0 = time.perf_counter()
-        O.features_batch(host[: max(1, min(cores, host.shape[0]))], ocfg, want=want)
+        O.features_batch(host[: max(1, min(cores, host.shape[0]))], ocfg, want=want, n_threads=cores)
         one = time.perf_counter() - t0
         reps = max(1, int(args.cpu_seconds / max(one, 1e-3)))
         n_cal = max(1, min(cores, host.shape[0]))
         t0 = time.perf_counter()
         for _ in range(reps):
-            O.features_batch(host[:n_cal], ocfg, want=want)
+            O.features_batch(host[:n_cal], ocfg, want=want, n_threads=cores)
         dtc = time.perf_counter() - t0
         cpu_baseline = {"value": n_cal * reps * CLIP_SECONDS / dtc, "unit": "audio-s/s", "cores": cores, "kind": "port",
                         "sample": f"{n_cal * reps} synthetic 5 s clips ({dtc:.1f} s), C port of src/dsp (complex128 radix-2), OpenMP over clips"}

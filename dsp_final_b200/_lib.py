@@ -72,8 +72,11 @@ _SIGNATURES = {
     "dspx_plan_read_table": (_I32, [_VP, _I32, _VP, _I64]),
     "dspx_stft": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP, _VP]),
     "dspx_features": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP]),
+    "dspx_log_mel_nchw": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "dspx_embed_stats": (_I32, [_VP, _I64, _I64, _I32, _VP, _VP]),
     "dspx_features_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP]),
+    "dspx_pcm16_to_float": (_I32, [_VP, _I64, _I64, _I64, _I32, _VP, _I64, _VP]),
+    "dspx_features_host_pcm16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP, _VP, _VP]),
     "dspx_stft_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP]),
     "dspx_next_pow_two": (_I64, [_I64]),
     "dspx_fft_c2c": (_I32, [_VP, _I64, _I64, _I64, _I32, _VP, _VP, _VP]),

@@ -51,19 +51,44 @@ def _want(want: Iterable[str]) -> tuple[str, ...]:
     return w
 
 
+def _is_pcm16(clips) -> bool:
+    dt = getattr(clips, "dtype", None)
+    return dt is not None and str(dt) in ("int16", "torch.int16")
+
+
+def pcm16_to_float(pcm, normalize: bool = True):
+    """int16 PCM [B, L] on the GPU -> float32 [B, L]: x/32768, then x/max|x| (src/utils/audio.py:19-38)."""
+    import torch
+
+    _lib.require_device()
+    x = pcm if pcm.dim() == 2 else pcm[None, :]
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    dev = x.device.index
+    with torch.cuda.device(dev):
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().dspx_pcm16_to_float(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0),
+                                                   1 if normalize else 0, out.data_ptr(), out.stride(0),
+                                                   torch.cuda.current_stream(dev).cuda_stream), "dspx_pcm16_to_float")
+    return out
+
+
 def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int | None = None,
-                   kernel: str = "auto") -> dict:
+                   kernel: str = "auto", normalize: bool = True) -> dict:
     """log-mel / MFCC / clip embeddings of a batch of equal-length clips.
 
     Follows src/dsp/mfcc.py:86-109 (+ src/retrieval/retrieval.py:19-23 for "embed").
     Returns {"log_mel": [B,T,n_mels], "mfcc": [B,T,n_mfcc], "embed": [B,2*n_mfcc]} (float32)
-    restricted to `want`.
+    restricted to `want`.  int16 input is taken as PCM16 and converted on the GPU like
+    load_audio (+ normalize_audio when `normalize`), src/utils/audio.py:19-38, cache.py:66-67.
     """
     want = _want(want)
     lib = _lib.load()
     if _is_cuda_tensor(clips):
         import torch
 
+        if _is_pcm16(clips):
+            clips = pcm16_to_float(clips, normalize)
         x = clips if clips.dim() == 2 else clips[None, :]
         if x.dtype != torch.float32 or x.stride(1) != 1:
             x = x.to(torch.float32).contiguous()
@@ -90,17 +115,28 @@ def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int
             out["embed"] = em
         return out
 
-    x = _as_host_clips(clips)
+    pcm = _is_pcm16(clips)
+    if pcm:
+        x = np.asarray(clips.numpy() if type(clips).__module__.startswith("torch") else clips)
+        x = x[None, :] if x.ndim == 1 else x
+        if x.strides[1] != 2 or x.strides[0] < 2 * x.shape[1] or x.strides[0] % 2:
+            x = np.ascontiguousarray(x)
+    else:
+        x = _as_host_clips(clips)
     plan = get_plan(cfg, device, kernel)
     b, length = x.shape
     t = plan.num_frames(length)
     lm = np.empty((b, t, plan.n_mels), np.float32) if "log_mel" in want else None
     mf = np.empty((b, t, plan.n_mfcc), np.float32) if "mfcc" in want else None
     em = np.empty((b, 2 * plan.n_mfcc), np.float32) if "embed" in want else None
-    _lib.check(lib.dspx_features_host(plan.handle, x.ctypes.data, b, length, max(x.strides[0] // 4, length),
-                                      lm.ctypes.data if lm is not None else None,
-                                      mf.ctypes.data if mf is not None else None,
-                                      em.ctypes.data if em is not None else None), "dspx_features_host")
+    outs = (lm.ctypes.data if lm is not None else None, mf.ctypes.data if mf is not None else None,
+            em.ctypes.data if em is not None else None)
+    if pcm:
+        _lib.check(lib.dspx_features_host_pcm16(plan.handle, x.ctypes.data, b, length, max(x.strides[0] // 2, length),
+                                                1 if normalize else 0, *outs), "dspx_features_host_pcm16")
+    else:
+        _lib.check(lib.dspx_features_host(plan.handle, x.ctypes.data, b, length, max(x.strides[0] // 4, length),
+                                          *outs), "dspx_features_host")
     out = {}
     if lm is not None:
         out["log_mel"] = lm
@@ -122,6 +158,32 @@ def log_mel_batch(clips, cfg, **kw):
 def mfcc_embed_batch(clips, cfg, **kw):
     """[B, 2*n_mfcc] clip embeddings, src/retrieval/retrieval.py:19-23 batched."""
     return features_batch(clips, cfg, ("embed",), **kw)["embed"]
+
+
+def log_mel_nchw(clips, cfg, device: int | None = None, kernel: str = "auto"):
+    """log-mel as the CNN input tensor [B, 1, n_mels, n_frames] (float32, torch CUDA in and out).
+
+    What LogMelTransform + DataLoader batching hand to ResNetAudio (src/train/transforms.py:16-18,
+    scripts/models/train_cnn.py:46-55), written in that layout by the kernel's store epilogue.
+    """
+    import torch
+
+    if not _is_cuda_tensor(clips):
+        clips = torch.as_tensor(_as_host_clips(clips)).cuda()
+    if _is_pcm16(clips):
+        clips = pcm16_to_float(clips)
+    x = clips if clips.dim() == 2 else clips[None, :]
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.to(torch.float32).contiguous()
+    dev = x.device.index if device is None else device
+    plan = get_plan(cfg, dev, kernel)
+    b, length = x.shape
+    t = plan.num_frames(length)
+    with torch.cuda.device(dev):
+        out = torch.empty((b, 1, plan.n_mels, t), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().dspx_log_mel_nchw(plan.handle, x.data_ptr(), b, length, x.stride(0), out.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream), "dspx_log_mel_nchw")
+    return out
 
 
 def stft_batch(clips, frame_length: int, hop_length: int, window: str = "hann", n_fft: int | None = None,

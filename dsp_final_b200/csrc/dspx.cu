@@ -12,6 +12,7 @@
 #include "feat_warp8.cuh"
 #include "fft_generic.cuh"
 #include "retrieval.cuh"
+#include "ingest.cuh"
 
 // the ctypes binding (dsp_final_b200/_lib.py) mirrors these layouts; tests assert the same numbers
 static_assert(sizeof(dspx_config) == 56 && offsetof(dspx_config, f_min) == 24 && offsetof(dspx_config, window) == 48,
@@ -64,7 +65,8 @@ struct HostPipe {
     void *d_out[PIPE_SLOTS] = {nullptr, nullptr, nullptr};
     void *h_in[PIPE_SLOTS] = {nullptr, nullptr, nullptr};    // pinned staging (pageable callers)
     void *h_out[PIPE_SLOTS] = {nullptr, nullptr, nullptr};
-    size_t in_bytes = 0, out_bytes = 0, hin_bytes = 0, hout_bytes = 0;
+    void *d_f32[PIPE_SLOTS] = {nullptr, nullptr, nullptr};   // float32 clips converted from PCM16
+    size_t in_bytes = 0, out_bytes = 0, hin_bytes = 0, hout_bytes = 0, f32_bytes = 0;
     void release()
     {
         for (int i = 0; i < PIPE_SLOTS; i++) {
@@ -72,11 +74,13 @@ struct HostPipe {
             if (d_out[i]) cudaFree(d_out[i]);
             if (h_in[i]) cudaFreeHost(h_in[i]);
             if (h_out[i]) cudaFreeHost(h_out[i]);
+            if (d_f32[i]) cudaFree(d_f32[i]);
+            d_f32[i] = nullptr;
             if (stream[i]) cudaStreamDestroy(stream[i]);
             d_in[i] = d_out[i] = h_in[i] = h_out[i] = nullptr;
             stream[i] = nullptr;
         }
-        in_bytes = out_bytes = hin_bytes = hout_bytes = 0;
+        in_bytes = out_bytes = hin_bytes = hout_bytes = f32_bytes = 0;
     }
 };
 
@@ -105,7 +109,7 @@ static void plan_free_device(dspx_plan *p)
 // ---- launch helpers ----------------------------------------------------------------
 static int launch_generic(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                           int64_t clip_stride, int64_t T, int take, int pre, float *logmel, float *mfcc,
-                          float2 *stft, cudaStream_t st)
+                          float2 *stft, cudaStream_t st, int nchw = 0)
 {
     GenParams gp{};
     gp.clips = clips;
@@ -145,6 +149,8 @@ static int launch_generic(const dspx_plan *pl, const float *clips, int64_t n_cli
     gp.fb_w = pl->d_fb_w;
     gp.dct2 = pl->d_dct2;
     gp.logmel = logmel;
+    gp.lm_ts = nchw ? 1 : pl->cfg.n_mels;
+    gp.lm_fs = nchw ? T : 1;
     gp.mfcc = mfcc;
     gp.stft = stft;
     const size_t smem = gen_smem_bytes(G, pl->M, gp.n_mels);
@@ -157,10 +163,10 @@ static int launch_generic(const dspx_plan *pl, const float *clips, int64_t n_cli
 }
 
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
-                            int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st)
+                            int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw)
 {
     return launch_generic(pl, clips, n_clips, clip_len, clip_stride, T, pl->take_feat,
-                          pl->cfg.pre_emphasis > 0.0 ? 1 : 0, logmel, mfcc, nullptr, st);
+                          pl->cfg.pre_emphasis > 0.0 ? 1 : 0, logmel, mfcc, nullptr, st, nchw);
 }
 
 static int launch_embed(const float *feats, int64_t n_clips, int64_t T, int C, float *out, cudaStream_t st)
@@ -175,22 +181,23 @@ static int launch_embed(const float *feats, int64_t n_clips, int64_t T, int C, f
 }
 
 static int features_device(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
-                           int64_t clip_stride, float *logmel, float *mfcc, float *embed, cudaStream_t st)
+                           int64_t clip_stride, float *logmel, float *mfcc, float *embed, cudaStream_t st, int nchw = 0)
 {
     const int64_t T = dspx_num_frames(pl, clip_len);
     if (T < 0) return DSPX_EINVAL;
     int rc;
     if (pl->kernel == DSPX_KERNEL_WARP8)
-        rc = launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st);
+        rc = launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
     else
         rc = launch_generic(pl, clips, n_clips, clip_len, clip_stride, T, pl->take_feat,
-                            pl->cfg.pre_emphasis > 0.0 ? 1 : 0, logmel, mfcc, nullptr, st);
+                            pl->cfg.pre_emphasis > 0.0 ? 1 : 0, logmel, mfcc, nullptr, st, nchw);
     if (rc != DSPX_OK) return rc;
     if (embed) rc = launch_embed(mfcc, n_clips, T, pl->cfg.n_mfcc, embed, st);
     return rc;
 }
 
-static int ensure_pipe(dspx_plan *pl, size_t in_bytes, size_t out_bytes, bool stage_in, bool stage_out, HostPipe **out)
+static int ensure_pipe(dspx_plan *pl, size_t in_bytes, size_t out_bytes, bool stage_in, bool stage_out, HostPipe **out,
+                       size_t f32_bytes = 0)
 {
     if (!pl->host_pipe) pl->host_pipe = new (std::nothrow) HostPipe();
     auto *hp = static_cast<HostPipe *>(pl->host_pipe);
@@ -213,6 +220,14 @@ static int ensure_pipe(dspx_plan *pl, size_t in_bytes, size_t out_bytes, bool st
             DSPX_CUDA_CHECK(cudaMalloc(&hp->d_out[i], out_bytes));
         }
         hp->out_bytes = out_bytes;
+    }
+    if (f32_bytes > hp->f32_bytes) {
+        for (int i = 0; i < PIPE_SLOTS; i++) {
+            if (hp->d_f32[i]) cudaFree(hp->d_f32[i]);
+            hp->d_f32[i] = nullptr;
+            DSPX_CUDA_CHECK(cudaMalloc(&hp->d_f32[i], f32_bytes));
+        }
+        hp->f32_bytes = f32_bytes;
     }
     if (stage_in && in_bytes > hp->hin_bytes) {
         for (int i = 0; i < PIPE_SLOTS; i++) {
@@ -246,15 +261,18 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Chunked host pipeline shared by dspx_features_host and dspx_stft_host.
 // mode 0: features (logmel/mfcc/embed), mode 1: stft (complex out in `o_stft`).
-static int host_pipeline(dspx_plan *pl, int mode, const float *clips, int64_t n_clips, int64_t clip_len,
-                         int64_t clip_stride, int pre, float *o_logmel, float *o_mfcc, float *o_embed, float *o_stft)
+// elem = 4: float32 clips; elem = 2: PCM16 clips converted (and optionally peak-normalised) on the device.
+static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n_clips, int64_t clip_len,
+                         int64_t clip_stride, int pre, float *o_logmel, float *o_mfcc, float *o_embed, float *o_stft,
+                         int elem = 4, int normalize = 0)
 {
+    const char *clips = static_cast<const char *>(clips_v);
     const int64_t T = dspx_num_frames(pl, clip_len);
     if (T < 0) return DSPX_EINVAL;
     DSPX_REQUIRE(clips && n_clips >= 0 && clip_stride >= clip_len, "bad clip buffer arguments");
     if (n_clips == 0) return DSPX_OK;
     DeviceGuard guard(pl->device);
-    const size_t clip_bytes = (size_t)clip_len * sizeof(float);
+    const size_t clip_bytes = (size_t)clip_len * elem;
     const size_t lm_b = (mode == 0 && o_logmel) ? (size_t)T * pl->cfg.n_mels * 4 : 0;
     const bool need_mfcc = mode == 0 && (o_mfcc || o_embed);
     const size_t mf_b = need_mfcc ? (size_t)T * pl->cfg.n_mfcc * 4 : 0;
@@ -273,7 +291,8 @@ static int host_pipeline(dspx_plan *pl, int mode, const float *clips, int64_t n_
     const size_t off_st = off_em + align256(em_b * chunk);
     const size_t out_bytes = off_st + align256(st_b * chunk);
     HostPipe *hp = nullptr;
-    int rc = ensure_pipe(pl, clip_bytes * chunk, out_bytes, !in_pinned, !out_pinned, &hp);
+    int rc = ensure_pipe(pl, clip_bytes * chunk, out_bytes, !in_pinned, !out_pinned, &hp,
+                         elem == 2 ? (size_t)clip_len * 4 * chunk : 0);
     if (rc != DSPX_OK) return rc;
     std::lock_guard<std::mutex> lock(hp->mu);
 
@@ -298,16 +317,23 @@ static int host_pipeline(dspx_plan *pl, int mode, const float *clips, int64_t n_
         const int64_t cnt = (n_clips - first) < chunk ? (n_clips - first) : chunk;
         if ((rc = drain(slot)) != DSPX_OK) return rc;
         cudaStream_t st = hp->stream[slot];
-        float *d_clips = static_cast<float *>(hp->d_in[slot]);
+        void *d_raw = hp->d_in[slot];
         char *d_o = static_cast<char *>(hp->d_out[slot]);
-        const float *src = clips + (size_t)first * clip_stride;
+        const char *src = clips + (size_t)first * clip_stride * elem;
         if (in_pinned) {
-            DSPX_CUDA_CHECK(cudaMemcpy2DAsync(d_clips, clip_bytes, src, (size_t)clip_stride * 4, clip_bytes, (size_t)cnt,
+            DSPX_CUDA_CHECK(cudaMemcpy2DAsync(d_raw, clip_bytes, src, (size_t)clip_stride * elem, clip_bytes, (size_t)cnt,
                                               cudaMemcpyHostToDevice, st));
         } else {
             char *h = static_cast<char *>(hp->h_in[slot]);
-            for (int64_t c = 0; c < cnt; c++) memcpy(h + (size_t)c * clip_bytes, src + (size_t)c * clip_stride, clip_bytes);
-            DSPX_CUDA_CHECK(cudaMemcpyAsync(d_clips, h, clip_bytes * cnt, cudaMemcpyHostToDevice, st));
+            for (int64_t c = 0; c < cnt; c++) memcpy(h + (size_t)c * clip_bytes, src + (size_t)c * clip_stride * elem, clip_bytes);
+            DSPX_CUDA_CHECK(cudaMemcpyAsync(d_raw, h, clip_bytes * cnt, cudaMemcpyHostToDevice, st));
+        }
+        float *d_clips = static_cast<float *>(d_raw);
+        if (elem == 2) {
+            d_clips = static_cast<float *>(hp->d_f32[slot]);
+            pcm16_to_float_kernel<<<(unsigned)cnt, 256, 0, st>>>(static_cast<const int16_t *>(d_raw), clip_len, clip_len,
+                                                                 normalize, d_clips, clip_len);
+            DSPX_CUDA_CHECK(cudaGetLastError());
         }
         float *d_lm = lm_b ? reinterpret_cast<float *>(d_o) : nullptr;
         float *d_mf = mf_b ? reinterpret_cast<float *>(d_o + off_mf) : nullptr;
@@ -530,6 +556,18 @@ int dspx_features(const dspx_plan *plan, const float *clips_dev, int64_t n_clips
                            static_cast<cudaStream_t>(stream));
 }
 
+int dspx_log_mel_nchw(const dspx_plan *plan, const float *clips_dev, int64_t n_clips, int64_t clip_len,
+                      int64_t clip_stride, float *out_dev, void *stream)
+{
+    DSPX_REQUIRE(plan && clips_dev && out_dev, "null argument");
+    DSPX_REQUIRE(n_clips >= 0 && clip_stride >= clip_len, "bad clip buffer arguments");
+    if (dspx_num_frames(plan, clip_len) < 0) return DSPX_EINVAL;
+    if (n_clips == 0) return DSPX_OK;
+    DeviceGuard guard(plan->device);
+    return features_device(plan, clips_dev, n_clips, clip_len, clip_stride, out_dev, nullptr, nullptr,
+                           static_cast<cudaStream_t>(stream), 1);
+}
+
 int dspx_embed_stats(const float *feats_dev, int64_t n_clips, int64_t n_frames, int n_coef, float *out_dev, void *stream)
 {
     DSPX_REQUIRE(feats_dev && out_dev, "null argument");
@@ -545,6 +583,29 @@ int dspx_features_host(const dspx_plan *plan, const float *clips_host, int64_t n
     DSPX_REQUIRE(logmel_out_host || mfcc_out_host || embed_out_host, "no output requested");
     return host_pipeline(const_cast<dspx_plan *>(plan), 0, clips_host, n_clips, clip_len, clip_stride, 0,
                          logmel_out_host, mfcc_out_host, embed_out_host, nullptr);
+}
+
+int dspx_pcm16_to_float(const int16_t *pcm_dev, int64_t n_clips, int64_t clip_len, int64_t pcm_stride, int normalize,
+                        float *out_dev, int64_t out_stride, void *stream)
+{
+    DSPX_REQUIRE(pcm_dev && out_dev, "null argument");
+    DSPX_REQUIRE(n_clips >= 0 && clip_len > 0 && pcm_stride >= clip_len && out_stride >= clip_len, "bad clip buffer arguments");
+    DSPX_REQUIRE(n_clips < (int64_t)2147483647, "too many clips for one launch");
+    if (n_clips == 0) return DSPX_OK;
+    pcm16_to_float_kernel<<<(unsigned)n_clips, 256, 0, static_cast<cudaStream_t>(stream)>>>(pcm_dev, clip_len, pcm_stride,
+                                                                                            normalize ? 1 : 0, out_dev, out_stride);
+    DSPX_CUDA_CHECK(cudaGetLastError());
+    return DSPX_OK;
+}
+
+int dspx_features_host_pcm16(const dspx_plan *plan, const int16_t *pcm_host, int64_t n_clips, int64_t clip_len,
+                             int64_t pcm_stride, int normalize, float *logmel_out_host, float *mfcc_out_host,
+                             float *embed_out_host)
+{
+    DSPX_REQUIRE(plan, "null plan");
+    DSPX_REQUIRE(logmel_out_host || mfcc_out_host || embed_out_host, "no output requested");
+    return host_pipeline(const_cast<dspx_plan *>(plan), 0, pcm_host, n_clips, clip_len, pcm_stride, 0, logmel_out_host,
+                         mfcc_out_host, embed_out_host, nullptr, 2, normalize ? 1 : 0);
 }
 
 int dspx_stft_host(const dspx_plan *plan, const float *clips_host, int64_t n_clips, int64_t clip_len, int64_t clip_stride,

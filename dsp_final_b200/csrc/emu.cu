@@ -103,6 +103,8 @@ int emu_features_generic(const dspx_config *cfg, const float *clips, int64_t n_c
     p.fb_w = e.t.fb_w.data();
     p.dct2 = e.dct2.data();
     p.logmel = logmel;
+    p.lm_ts = p.n_mels;
+    p.lm_fs = 1;
     p.mfcc = mfcc;
     p.stft = stft_mode ? reinterpret_cast<float2 *>(stft_out) : nullptr;
 
@@ -171,6 +173,8 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     p.tables = blob.data();
     p.logmel = logmel;
     p.mfcc = mfcc;
+    p.lm_ts = p.n_mels;
+    p.lm_fs = 1;
     const bool pre = cfg->pre_emphasis > 0.0;
     std::vector<float> warp_smem(w8_warp_floats(tb, p.n_mels) + 4, 0.f);
     W8Ctx c;

@@ -44,6 +44,7 @@ struct GenParams {
     const float *fb_w;
     const float *dct2;
     float *logmel;          // may be null
+    int64_t lm_ts, lm_fs;   // log-mel strides between frames / between filters ([B,T,M]: M,1; [B,1,M,T]: 1,T)
     float *mfcc;            // may be null
     float2 *stft;           // non-null selects complex-spectrum output (no mel stages)
 };
@@ -179,7 +180,7 @@ DSPX_HD void gen_phase_logmel(const GenParams &p, const float *part, float *lm, 
     const float v = logf(fmaxf(s, 1e-10f));
     lm[i] = v;
     const int64_t t = t0 + g;
-    if (p.logmel && t < p.n_frames) p.logmel[((size_t)clip_idx * p.n_frames + t) * p.n_mels + f] = v;
+    if (p.logmel && t < p.n_frames) p.logmel[(size_t)clip_idx * p.n_frames * p.n_mels + t * p.lm_ts + f * p.lm_fs] = v;
 }
 
 // phase 6: items [0, G*n_mfcc): DCT-II (table already carries the factor 2)

@@ -127,6 +127,7 @@ struct W8Params {
     W8Tables tb;
     const float *tables;     // global copy of the blob
     float *logmel, *mfcc;    // either may be null
+    int64_t lm_ts, lm_fs;    // log-mel strides between frames / filters ([B,T,M]: M,1; [B,1,M,T]: 1,T)
 };
 
 struct W8Ctx {               // everything one warp needs for one frame pair
@@ -143,6 +144,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     float alpha;
     int n_mels, n_mfcc, rounds, cw_lanes, validB;
     float *logmelA, *logmelB, *mfccA, *mfccB;   // rows of the two frames (null when not requested)
+    int64_t lm_fs;
 };
 
 struct W8Power {             // |X|^2 of the bins one lane owns, carried across the syncwarp
@@ -378,8 +380,8 @@ DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
         const float2 v = make_float2(w8_log(fmaxf(s.x, 1e-10f)), w8_log(fmaxf(s.y, 1e-10f)));
         c.lm[f] = v;
         if (c.logmelA) {
-            c.logmelA[f] = v.x;
-            if (c.validB) c.logmelB[f] = v.y;
+            c.logmelA[f * c.lm_fs] = v.x;
+            if (c.validB) c.logmelB[f * c.lm_fs] = v.y;
         }
     }
 }
@@ -423,8 +425,9 @@ DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
     c.firstA = pair == 0;
     c.firstB = c.validB ? 0 : c.firstA;        // a missing frame B replays frame A
     const int64_t rowA = (int64_t)clip * p.n_frames + tA, rowB = rowA + 1;
-    c.logmelA = p.logmel ? p.logmel + rowA * p.n_mels : nullptr;
-    c.logmelB = p.logmel ? p.logmel + rowB * p.n_mels : nullptr;
+    c.logmelA = p.logmel ? p.logmel + (int64_t)clip * p.n_frames * p.n_mels + tA * p.lm_ts : nullptr;
+    c.logmelB = c.logmelA ? c.logmelA + p.lm_ts : nullptr;
+    c.lm_fs = p.lm_fs;
     c.mfccA = p.mfcc ? p.mfcc + rowA * p.n_mfcc : nullptr;
     c.mfccB = p.mfcc ? p.mfcc + rowB * p.n_mfcc : nullptr;
 }
@@ -649,15 +652,15 @@ inline void warp8_release(dspx_plan *pl)
 }
 
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
-                            int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st);
+                            int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
 
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
-                        int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st)
+                        int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw = 0)
 {
     const int64_t pairs = (T + 1) / 2;
     // 8-byte vector loads need even row strides and an 8-byte aligned base; items are 32-bit
     if ((clip_stride & 1) || (reinterpret_cast<uintptr_t>(clips) & 7) || n_clips * pairs >= (int64_t)0x7fffffff)
-        return launch_generic_fallback(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st);
+        return launch_generic_fallback(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
     const W8PlanData *pd = static_cast<const W8PlanData *>(pl->fast_host);
     W8Params p{};
     p.clips = clips;
@@ -675,6 +678,8 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.tables = static_cast<const float *>(pl->d_fast_tables);
     p.logmel = logmel;
     p.mfcc = mfcc;
+    p.lm_ts = nchw ? 1 : p.n_mels;
+    p.lm_fs = nchw ? T : 1;
     int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
     const int64_t resident = (int64_t)pl->sm_count * pd->ctas_per_sm;
     if (ctas > resident) ctas = resident;                    // persistent: warps stride over the items

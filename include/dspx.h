@@ -113,6 +113,13 @@ int dspx_features(const dspx_plan *plan, const float *clips_dev, int64_t n_clips
                   int64_t clip_stride, float *logmel_out_dev, float *mfcc_out_dev,
                   float *embed_out_dev, void *stream);
 
+/* log-mel written directly in the CNN input layout [n_clips, 1, n_mels, n_frames] that
+ * LogMelTransform / train_cnn build with feat.T[None] (src/train/transforms.py:16-18,
+ * scripts/models/train_cnn.py:46-47): same values as dspx_features' log-mel, transposed in the
+ * store epilogue. */
+int dspx_log_mel_nchw(const dspx_plan *plan, const float *clips_dev, int64_t n_clips, int64_t clip_len,
+                      int64_t clip_stride, float *out_dev, void *stream);
+
 /* dct_type_2(x, n_mfcc), src/dsp/mfcc.py:73-83, for callers that hold their own log-mel
  * rows (scripts/tools/plot_dsp_viz.py): x [rows, n] f32 -> out [rows, n_mfcc] f32,
  * out[r,k] = 2 * sum_j x[r,j] cos(pi/n (j+0.5) k). */
@@ -131,6 +138,16 @@ int dspx_features_host(const dspx_plan *plan, const float *clips_host, int64_t n
                        float *mfcc_out_host, float *embed_out_host);
 int dspx_stft_host(const dspx_plan *plan, const float *clips_host, int64_t n_clips,
                    int64_t clip_len, int64_t clip_stride, int pre_emphasis, float *out_host);
+
+/* ---- PCM16 ingest: load_audio + normalize_audio, src/utils/audio.py:19-38 ----
+ * x = int16 / 32768 (what soundfile returns for dtype="float32"), then x / max|x| when normalize
+ * != 0 and the clip is not all zero -- the correctly rounded float32 quotient, i.e. bit-identical
+ * to NumPy.  The _host form ships int16 over PCIe (half the bytes of float32 clips). */
+int dspx_pcm16_to_float(const int16_t *pcm_dev, int64_t n_clips, int64_t clip_len, int64_t pcm_stride,
+                        int normalize, float *out_dev, int64_t out_stride, void *stream);
+int dspx_features_host_pcm16(const dspx_plan *plan, const int16_t *pcm_host, int64_t n_clips,
+                             int64_t clip_len, int64_t pcm_stride, int normalize,
+                             float *logmel_out_host, float *mfcc_out_host, float *embed_out_host);
 
 /* ---- fft / ifft / rfft  src/dsp/fft.py:27-77 ----
  * in_dev [batch, n_in] interleaved complex64; the first min(n_in, n) samples are used,

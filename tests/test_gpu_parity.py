@@ -311,3 +311,68 @@ def test_retrieval_sweep_config3(torch_cuda):
             for k in (10, 20):
                 ours = R.hits_at_k(idx, k, targets[folds <= 4], targets[folds == 5])
                 assert ours == O.hits_at_k(idx, k, targets[folds <= 4], targets[folds == 5])
+
+
+def test_pcm16_ingest_matches_load_audio_semantics(torch_cuda, golden_real):
+    """Row f2: int16 in -> x/32768 -> x/max|x| on the GPU == NumPy float32, bit for bit; features follow."""
+    torch = torch_cuda
+    from dsp_final_b200.batch import features_batch, pcm16_to_float
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+
+    g = golden_real
+    rng = np.random.default_rng(3)
+    pcm = np.stack([g["pcm16"][:40_000], (rng.standard_normal(40_000) * 3000).astype(np.int16),
+                    np.zeros(40_000, np.int16)])
+    pcm[1, 123] = -32768                                          # |min int16| is the peak
+    x = pcm.astype(np.float32) / np.float32(32768.0)
+    peak = np.max(np.abs(x), axis=1, keepdims=True)
+    xn = np.where(peak > 0, x / np.where(peak > 0, peak, 1), x).astype(np.float32)
+    dev = pcm16_to_float(torch.as_tensor(pcm).cuda(), normalize=True).cpu().numpy()
+    assert np.array_equal(dev, xn)
+    assert np.array_equal(pcm16_to_float(torch.as_tensor(pcm).cuda(), normalize=False).cpu().numpy(), x)
+    cfg = MfccConfig(sample_rate=44100, frame_length=1024, hop_length=512)
+    want = features_batch(xn, cfg, ("mfcc", "log_mel", "embed"))
+    for src in (pcm, torch.as_tensor(pcm).cuda()):
+        got = features_batch(src, cfg, ("mfcc", "log_mel", "embed"))
+        for k in want:
+            a = got[k].cpu().numpy() if hasattr(got[k], "cpu") else got[k]
+            assert np.array_equal(a, want[k]), k
+    # the real-clip golden (reference features of the normalised excerpt) through the PCM16 door
+    full = features_batch(g["pcm16"][None, :], cfg, ("mfcc",))["mfcc"][0]
+    _close(full, g["mfcc"], "pcm16 real clip mfcc")
+
+
+@pytest.mark.parametrize("kernel,fl", [("auto", 1024), ("generic", 1024), ("auto", 512)])
+def test_log_mel_cnn_layout(torch_cuda, kernel, fl):
+    """Row f3: [B,1,n_mels,T] written by the store epilogue == transpose of the reference layout."""
+    torch = torch_cuda
+    from dsp_final_b200 import synth
+    from dsp_final_b200.batch import features_batch, log_mel_nchw
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+
+    cfg = MfccConfig(sample_rate=44100, frame_length=fl, hop_length=fl // 2, n_mels=128)
+    dev = torch.as_tensor(synth.host_clips(5, seed=4, length=50_001)).cuda()     # odd frame count
+    ref = features_batch(dev, cfg, ("log_mel",), kernel=kernel)["log_mel"]
+    out = log_mel_nchw(dev, cfg, kernel=kernel)
+    assert out.shape == (5, 1, 128, ref.shape[1]) and out.is_contiguous()
+    assert torch.equal(out[:, 0], ref.transpose(1, 2))
+
+
+@pytest.mark.parametrize("dim", [128, 512, 768, 2048])
+def test_retrieval_ml_dimensions(torch_cuda, dim):
+    """Row f4: model-embedding dimensions of retrieval_ml.py through the same kernels, bit-exact indices."""
+    from types import SimpleNamespace
+
+    from dsp_final_b200 import retrieval_ml as RM
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(dim)
+    db = rng.standard_normal((1600, dim)).astype(np.float32)
+    q = rng.standard_normal((400, dim)).astype(np.float32)
+    tdb, tq = rng.integers(0, 50, 1600), rng.integers(0, 50, 400)
+    idx = RM.cosine_topk(q, db, 20)
+    assert np.array_equal(idx, O.cosine_topk(q, db, 20))
+    items = lambda t: [SimpleNamespace(target=int(v)) for v in t]   # noqa: E731
+    res = RM.evaluate_retrieval(items(tdb), items(tq), db, q, (10, 20))
+    want = O.evaluate_retrieval(tdb, tq, db, q, (10, 20))
+    assert [(r.k, r.precision) for r in res] == want
