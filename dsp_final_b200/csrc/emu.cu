@@ -187,16 +187,33 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     c.n_mfcc = p.n_mfcc;
     c.rounds = tb.rounds;
     c.cw_lanes = tb.cw_lanes;
-    std::vector<W8Power> pw(32);
+    const int r1 = tb.r1;
+    const int units = r1 >= 8 ? r1 / 8 : 1;
+    std::vector<W8Power> pw(32 * 2);
     for (uint32_t item = 0; item < p.n_items; item++) {
         w8_set_item(p, c, item);
         for (int lane = 0; lane < 32; lane++) {
-            if (pre) w8_pass1<true>(c, lane);
-            else w8_pass1<false>(c, lane);
+            if (r1 == 4) { if (pre) w8_pass1<4, true>(c, lane); else w8_pass1<4, false>(c, lane); }
+            else if (r1 == 8) { if (pre) w8_pass1<8, true>(c, lane); else w8_pass1<8, false>(c, lane); }
+            else { if (pre) w8_pass1<16, true>(c, lane); else w8_pass1<16, false>(c, lane); }
         }
-        for (int lane = 0; lane < 32; lane++) w8_pass2(c, lane);
-        for (int lane = 0; lane < 32; lane++) w8_pass3(c, lane, pw[lane]);
-        for (int lane = 0; lane < 32; lane++) w8_store_power(c, lane, pw[lane]);
+        for (int lane = 0; lane < 32; lane++) {
+            if (r1 == 4) w8_pass2<4>(c, lane);
+            else if (r1 == 8) w8_pass2<8>(c, lane);
+            else w8_pass2<16>(c, lane);
+        }
+        for (int lane = 0; lane < 32; lane++)
+            for (int w = 0; w < units; w++) {
+                if (r1 == 4) w8_pass3<4>(c, lane, w, pw[lane * 2 + w]);
+                else if (r1 == 8) w8_pass3<8>(c, lane, w, pw[lane * 2 + w]);
+                else w8_pass3<16>(c, lane, w, pw[lane * 2 + w]);
+            }
+        for (int lane = 0; lane < 32; lane++)
+            for (int w = 0; w < units; w++) {
+                if (r1 == 4) w8_store_power<4>(c, lane, w, pw[lane * 2 + w]);
+                else if (r1 == 8) w8_store_power<8>(c, lane, w, pw[lane * 2 + w]);
+                else w8_store_power<16>(c, lane, w, pw[lane * 2 + w]);
+            }
         for (int lane = 0; lane < 32; lane++) w8_mel_chunks(c, lane);
         for (int lane = 0; lane < 32; lane++) w8_logmel(c, lane);
         if (c.mfccA) {

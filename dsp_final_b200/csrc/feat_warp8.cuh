@@ -104,18 +104,79 @@ DSPX_HD void dft8(float2 (&re)[8], float2 (&im)[8])
     }
 }
 
+// 4-point forward DFT (8 packed adds)
+DSPX_HD void dft4(float2 (&re)[4], float2 (&im)[4])
+{
+    const float2 s02r = add2(re[0], re[2]), s02i = add2(im[0], im[2]);
+    const float2 d02r = sub2(re[0], re[2]), d02i = sub2(im[0], im[2]);
+    const float2 s13r = add2(re[1], re[3]), s13i = add2(im[1], im[3]);
+    const float2 d13r = sub2(im[1], im[3]), d13i = sub2(re[3], re[1]);      // (v1 - v3) * (-i)
+    re[0] = add2(s02r, s13r); im[0] = add2(s02i, s13i);
+    re[1] = add2(d02r, d13r); im[1] = add2(d02i, d13i);
+    re[2] = sub2(s02r, s13r); im[2] = sub2(s02i, s13i);
+    re[3] = sub2(d02r, d13r); im[3] = sub2(d02i, d13i);
+}
+
+// 16-point forward DFT = 4 x 4: DFT-4 over n2 (n = n1 + 4 n2), twiddle W16^(n1 k2), DFT-4 over n1;
+// output X[k2 + 4 k1].  Natural order in and out.
+DSPX_HD void dft16(float2 (&re)[16], float2 (&im)[16])
+{
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    float2 yr[4][4], yi[4][4];                       // [n1][k2]
+#pragma unroll
+    for (int n1 = 0; n1 < 4; n1++) {
+        float2 tr[4] = {re[n1], re[n1 + 4], re[n1 + 8], re[n1 + 12]};
+        float2 ti[4] = {im[n1], im[n1 + 4], im[n1 + 8], im[n1 + 12]};
+        dft4(tr, ti);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) { yr[n1][k2] = tr[k2]; yi[n1][k2] = ti[k2]; }
+    }
+    // twiddles W16^(n1 k2) = exp(-2 pi i n1 k2 / 16): (cos, -sin)
+    cmul2(yr[1][1], yi[1][1], c1, -s1);              // W^1
+    cmul2(yr[1][2], yi[1][2], h, -h);                // W^2
+    cmul2(yr[1][3], yi[1][3], s1, -c1);              // W^3
+    cmul2(yr[2][1], yi[2][1], h, -h);                // W^2
+    { const float2 r = yi[2][2], i = neg2(yr[2][2]); yr[2][2] = r; yi[2][2] = i; }   // W^4 = -i
+    cmul2(yr[2][3], yi[2][3], -h, -h);               // W^6
+    cmul2(yr[3][1], yi[3][1], s1, -c1);              // W^3
+    cmul2(yr[3][2], yi[3][2], -h, -h);               // W^6
+    cmul2(yr[3][3], yi[3][3], -c1, s1);              // W^9 = -W^1
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) {
+        float2 tr[4] = {yr[0][k2], yr[1][k2], yr[2][k2], yr[3][k2]};
+        float2 ti[4] = {yi[0][k2], yi[1][k2], yi[2][k2], yi[3][k2]};
+        dft4(tr, ti);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) { re[k2 + 4 * k1] = tr[k1]; im[k2 + 4 * k1] = ti[k1]; }
+    }
+}
+
+DSPX_HD void dftn(float2 (&re)[4], float2 (&im)[4]) { dft4(re, im); }
+DSPX_HD void dftn(float2 (&re)[8], float2 (&im)[8]) { dft8(re, im); }
+DSPX_HD void dftn(float2 (&re)[16], float2 (&im)[16]) { dft16(re, im); }
+
 // exchange-tile address (in float4 units) of element (k_a, x, c): x = b before pass 2, k_b after
-DSPX_HD int w8_addr(int ka, int x, int c) { return ((ka * 8 + x) << 3) | (c ^ ka); }
+DSPX_HD int w8_addr(int ka, int x, int c) { return ((ka * 8 + x) << 3) | (c ^ (ka & 7)); }
 
 constexpr int W8_CHUNK = 8;               // bins per mel chunk
 constexpr int W8_CSTRIDE = 10;            // float2 slots per chunk in the power tile (80 B: conflict-free LDS.128)
 constexpr int W8_WROW = 20;               // floats per chunk row of the weight table (a0 b0 .. a7 b7 + pad)
+
+// Geometry for first-pass radix R1: M = 64 R1 complex points (n_fft = 128 R1), J = 8 R1 output residues.
+template <int R1> struct W8Geo {
+    static constexpr int M = 64 * R1, P = 128 * R1, J = 8 * R1;
+    static constexpr int LOG_R1 = R1 == 4 ? 2 : (R1 == 8 ? 3 : 4);
+    static constexpr int SETS2 = R1 / 4;                 // radix-8 transforms per lane in pass 2
+    static constexpr int UNITS = R1 >= 8 ? R1 / 8 : 1;   // mirror-pair units per lane in pass 3
+    static constexpr int ACTIVE3 = R1 >= 8 ? 32 : 16;    // lanes that own a unit in pass 3
+};
 
 struct W8Tables {            // offsets (in floats) into the packed table blob / shared memory
     int win, tw1, tw2, ptw, ppos, cw, cflag, fdesc, dct, total;
     int rounds, n_slots;     // mel chunks: 32 lanes x rounds (rounds odd)
     int cw_lanes;            // DCT: coefficient lanes per part (16 or 32)
     int tile_floats;         // per-warp exchange / power tile
+    int r1;                  // first-pass radix (4, 8, 16)
 };
 
 struct W8Params {
@@ -147,7 +208,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     int64_t lm_fs;
 };
 
-struct W8Power {             // |X|^2 of the bins one lane owns, carried across the syncwarp
+struct W8Power {             // |X|^2 of the bins one pass-3 unit owns, carried across the syncwarp
     float2 lo[9], hi[9];
 };
 
@@ -175,20 +236,20 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
     c.dsc = c.lm + n_mels;
 }
 
-// ---- phase A: load, pre-emphasis, window, radix-8 over a, twiddle, store -----------------
-// All 32 loads of a set are issued before the first use (memory-level parallelism); the only
+// ---- phase A: load, pre-emphasis, window, radix-R1 over a, twiddle, store -----------------
+// All loads of a set are issued before the first use (memory-level parallelism); the only
 // sample without a predecessor is sample 0 of a clip (y[0] = x[0], src/dsp/mfcc.py:88).
-template <bool PRE>
+template <int R1, bool PRE>
 DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 {
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         const int tid = lane + 32 * s;
         const float *pa = c.fa + 2 * tid, *pb = c.fb + 2 * tid;
-        float2 xa[8], xb[8];
-        float pva[8], pvb[8];
+        float2 xa[R1], xb[R1];
+        float pva[R1], pvb[R1];
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
+        for (int a = 0; a < R1; a++) {
             xa[a] = *reinterpret_cast<const float2 *>(pa + 128 * a);
             xb[a] = *reinterpret_cast<const float2 *>(pb + 128 * a);
         }
@@ -199,14 +260,14 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
             if (edgeA) pva[0] = 0.f;
             if (edgeB) pvb[0] = 0.f;
 #pragma unroll
-            for (int a = 1; a < 8; a++) {
+            for (int a = 1; a < R1; a++) {
                 pva[a] = pa[128 * a - 1];
                 pvb[a] = pb[128 * a - 1];
             }
         }
-        float2 re[8], im[8];
+        float2 re[R1], im[R1];
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
+        for (int a = 0; a < R1; a++) {
             float2 y0 = make_float2(xa[a].x, xb[a].x), y1 = make_float2(xa[a].y, xb[a].y);
             if (PRE) {
                 const float2 al = bc2(c.alpha);
@@ -214,15 +275,15 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
                 y1 = sub2(y1, t1);                                                          // ... rounded differences
                 y0 = sub2(y0, t0);
             }
-            const float2 w = c.win[(s * 8 + a) * 32 + lane];            // (0.5 w[n], 0.5 w[n+1])
+            const float2 w = c.win[(s * R1 + a) * 32 + lane];           // (0.5 w[n], 0.5 w[n+1])
             re[a] = mul2(y0, bc2(w.x));
             im[a] = mul2(y1, bc2(w.y));
         }
-        dft8(re, im);
+        dftn(re, im);
         c.xbuf[w8_addr(0, tid >> 3, tid & 7)] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
 #pragma unroll
-        for (int ka = 1; ka < 8; ka++) {
-            const float2 w = c.tw1[(s * 7 + ka - 1) * 32 + lane];       // exp(-2 pi i tid ka / 512)
+        for (int ka = 1; ka < R1; ka++) {
+            const float2 w = c.tw1[(s * (R1 - 1) + ka - 1) * 32 + lane];  // exp(-2 pi i tid ka / M)
             cmul2(re[ka], im[ka], w.x, w.y);
             c.xbuf[w8_addr(ka, tid >> 3, tid & 7)] = make_float4(re[ka].x, re[ka].y, im[ka].x, im[ka].y);
         }
@@ -230,11 +291,12 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 }
 
 // ---- phase B: radix-8 over b, in place, twiddle exp(-2 pi i c k_b / 64) ---------------------
+template <int R1>
 DSPX_HD void w8_pass2(const W8Ctx &c, int lane)
 {
     const int cc = lane & 7;
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < W8Geo<R1>::SETS2; s++) {
         const int ka = (lane >> 3) + 4 * s;
         float2 re[8], im[8];
 #pragma unroll
@@ -254,8 +316,8 @@ DSPX_HD void w8_pass2(const W8Ctx &c, int lane)
     }
 }
 
-// packed-real split of one mirror pair (a = Z[k], b = Z[512-k]); the window carries the 1/2:
-//   E = a + conj b, O = -i (a - conj b), T = W^k O, |X[k]|^2 = |E + T|^2, |X[512-k]|^2 = |E - T|^2
+// packed-real split of one mirror pair (a = Z[k], b = Z[M-k]); the window carries the 1/2:
+//   E = a + conj b, O = -i (a - conj b), T = W^k O, |X[k]|^2 = |E + T|^2, |X[M-k]|^2 = |E - T|^2
 DSPX_HD void w8_split(float2 ar, float2 ai, float2 br, float2 bi, float2 w, float2 &plo, float2 &phi)
 {
     const float2 er = add2(ar, br), ei = sub2(ai, bi);
@@ -271,58 +333,67 @@ DSPX_HD void w8_split(float2 ar, float2 ai, float2 br, float2 bi, float2 w, floa
 
 DSPX_HD float2 sel2(bool p, float2 a, float2 b) { return p ? a : b; }
 
-// ---- phase C: radix-8 over c for residues j and 64-j, split, power ---------------------------
-DSPX_HD void w8_pass3(const W8Ctx &c, int lane, W8Power &pw)
+// bin index of slot m of pass-3 unit u (u = lane + 32 w); J = 8 R1 residues
+DSPX_HD int w8_bin(int J, int u, int m)
 {
-    const bool l0 = lane == 0;
-    const int j1 = lane, j2 = l0 ? 32 : 64 - lane;
+    const int k0[9] = {0, J, 2 * J, 3 * J, 4 * J, J / 2, J / 2 + J, J / 2 + 2 * J, J / 2 + 3 * J};
+    return u == 0 ? k0[m] : u + J * m;
+}
+
+// ---- phase C: radix-8 over c for residues j and J-j, split, power ---------------------------
+// unit u pairs Z[u + J m] with its mirror Z[M - u - J m] = D2[7 - m]; unit 0 owns the two
+// self-mirrored residues 0 and J/2: slots {0:(Z0,Z0) 1..3:(Z[Jm],Z[M-Jm]) 4:(Z[M/2],Z[M/2])
+// 5..7:(Z[J/2+Jq],Z[M-J/2-Jq]) q=0..2} and a ninth slot for q = 3.
+template <int R1>
+DSPX_HD void w8_pass3(const W8Ctx &c, int lane, int w, W8Power &pw)
+{
+    using G = W8Geo<R1>;
+    if (lane >= G::ACTIVE3) return;
+    const int u = lane + 32 * w;
+    const bool l0 = u == 0;
+    const int j1 = u, j2 = l0 ? G::J / 2 : G::J - u;
     float2 r1[8], i1[8], r2[8], i2[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-        const float4 v = c.xbuf[w8_addr(j1 & 7, j1 >> 3, q)];
+        const float4 v = c.xbuf[w8_addr(j1 & (R1 - 1), j1 >> G::LOG_R1, q)];
         r1[q] = make_float2(v.x, v.y);
         i1[q] = make_float2(v.z, v.w);
-        const float4 u = c.xbuf[w8_addr(j2 & 7, j2 >> 3, q)];
-        r2[q] = make_float2(u.x, u.y);
-        i2[q] = make_float2(u.z, u.w);
+        const float4 t = c.xbuf[w8_addr(j2 & (R1 - 1), j2 >> G::LOG_R1, q)];
+        r2[q] = make_float2(t.x, t.y);
+        i2[q] = make_float2(t.z, t.w);
     }
-    dft8(r1, i1);          // Z[j1 + 64 m]
-    dft8(r2, i2);          // Z[j2 + 64 m]
-    // lanes 1..31: slot m pairs Z[lane + 64 m] with Z[512 - lane - 64 m] = D2[7 - m].
-    // lane 0 owns the self-mirrored residues 0 and 32: slots {0:(Z0,Z0) 1..3:(Z[64m],Z[512-64m])
-    // 4:(Z256,Z256) 5..7:(Z[32+64q],Z[480-64q]) q=0..2} and a ninth slot (Z224, Z288).
+    dft8(r1, i1);          // Z[j1 + J m]
+    dft8(r2, i2);          // Z[j2 + J m]
+    const float2 *ptw = c.ptw + w * 9 * 32;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
         float2 ar = r1[m], ai = i1[m];
         if (m >= 5) { ar = sel2(l0, r2[m - 5], ar); ai = sel2(l0, i2[m - 5], ai); }
-        const int b0 = m == 0 ? 0 : (m <= 4 ? 8 - m : 0);               // lane-0 partner index in D1 (m <= 4)
+        const int b0 = m == 0 ? 0 : (m <= 4 ? 8 - m : 0);               // unit-0 partner index in D1 (m <= 4)
         float2 br, bi;
         if (m <= 4) { br = sel2(l0, r1[b0 & 7], r2[7 - m]); bi = sel2(l0, i1[b0 & 7], i2[7 - m]); }
         else { br = sel2(l0, r2[12 - m], r2[7 - m]); bi = sel2(l0, i2[12 - m], i2[7 - m]); }
-        w8_split(ar, ai, br, bi, c.ptw[m * 32 + lane], pw.lo[m], pw.hi[m]);
+        w8_split(ar, ai, br, bi, ptw[m * 32 + lane], pw.lo[m], pw.hi[m]);
     }
-    if (l0) w8_split(r2[3], i2[3], r2[4], i2[4], c.ptw[8 * 32], pw.lo[8], pw.hi[8]);
-}
-
-DSPX_HD int w8_bin(int lane, int m)      // bin index of slot m
-{
-    const int k0[9] = {0, 64, 128, 192, 256, 32, 96, 160, 224};
-    return lane == 0 ? k0[m] : lane + 64 * m;
+    if (l0) w8_split(r2[3], i2[3], r2[4], i2[4], ptw[8 * 32], pw.lo[8], pw.hi[8]);
 }
 
 // ---- phase D: power spectrum into the (re-used) tile, in mel-chunk order ---------------------------
-// ppos[m][lane] = tile slots of bins k_m and 512 - k_m: bins of one mel chunk are contiguous,
+// ppos[w][m][lane] = tile slots of bins k_m and M - k_m: bins of one mel chunk are contiguous,
 // chunks sit W8_CSTRIDE slots apart, bins no filter uses go to a dump slot.
-DSPX_HD void w8_store_power(const W8Ctx &c, int lane, const W8Power &pw)
+template <int R1>
+DSPX_HD void w8_store_power(const W8Ctx &c, int lane, int w, const W8Power &pw)
 {
+    if (lane >= W8Geo<R1>::ACTIVE3) return;
+    const int2 *ppos = c.ppos + w * 9 * 32;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
-        const int2 p = c.ppos[m * 32 + lane];
+        const int2 p = ppos[m * 32 + lane];
         c.pbuf[p.x] = pw.lo[m];
         c.pbuf[p.y] = pw.hi[m];
     }
-    if (lane == 0) {
-        const int2 p = c.ppos[8 * 32];
+    if (lane + 32 * w == 0) {
+        const int2 p = ppos[8 * 32];
         c.pbuf[p.x] = pw.lo[8];
         c.pbuf[p.y] = pw.hi[8];
     }
@@ -393,9 +464,7 @@ DSPX_HD void w8_dct_partial(const W8Ctx &c, int lane, int c0)
 {
     const int cwl = c.cw_lanes, parts = 32 / cwl;
     const int q = lane & (cwl - 1), part = lane / cwl;
-    const int blocks = (c.n_mfcc + cwl - 1) / cwl;
     const float *col = c.dct + (size_t)(c0 / cwl) * c.n_mels * cwl + q;     // block-major table
-    (void)blocks;
     float2 acc = make_float2(0.f, 0.f);
     for (int f = part; f < c.n_mels; f += parts) acc = fma2(c.lm[f], bc2(col[f * cwl]), acc);
     c.dsc[lane] = acc;
@@ -432,21 +501,23 @@ DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
     c.mfccB = p.mfcc ? p.mfcc + rowB * p.n_mfcc : nullptr;
 }
 
+// the whole per-item sequence; SYNC is __syncwarp() on the device and a no-op in the lane-loop replay
 #if defined(__CUDACC__)
 // pull the next item's samples towards L2 while this one is being transformed
-__device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, int lane)
+__device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, int lane, int n_fft)
 {
     if (item >= p.n_items) return;
     const uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
     const char *base = reinterpret_cast<const char *>(p.clips + (int64_t)clip * p.clip_stride + 2 * (int64_t)pair * p.hop);
-    const int span = (p.hop + 1024) * 4;                       // bytes covered by the frame pair
+    const int span = (p.hop + n_fft) * 4;                      // bytes covered by the frame pair
     for (int off = lane * 128; off < span; off += 32 * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-template <bool PRE>
-__global__ void __launch_bounds__(W8_WARPS * 32, 2) feat_warp8_kernel(const W8Params p)
+template <int R1, bool PRE>
+__global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_kernel(const W8Params p)
 {
+    using G = W8Geo<R1>;
     extern __shared__ __align__(16) float w8_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wf = w8_warp_floats(p.tb, p.n_mels);
@@ -470,15 +541,17 @@ __global__ void __launch_bounds__(W8_WARPS * 32, 2) feat_warp8_kernel(const W8Pa
     const uint32_t n_warps = gridDim.x * W8_WARPS;
     for (uint32_t item = blockIdx.x * W8_WARPS + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
-        w8_pass1<PRE>(c, lane);
-        if (p.prefetch) w8_prefetch(p, item + n_warps, lane);
+        w8_pass1<R1, PRE>(c, lane);
+        if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
-        w8_pass2(c, lane);
+        w8_pass2<R1>(c, lane);
         __syncwarp();
-        W8Power pw;
-        w8_pass3(c, lane, pw);
+        W8Power pw[G::UNITS];
+#pragma unroll
+        for (int w = 0; w < G::UNITS; w++) w8_pass3<R1>(c, lane, w, pw[w]);
         __syncwarp();                       // every lane has read its inputs: the tile may become P[]
-        w8_store_power(c, lane, pw);
+#pragma unroll
+        for (int w = 0; w < G::UNITS; w++) w8_store_power<R1>(c, lane, w, pw[w]);
         __syncwarp();
         w8_mel_chunks(c, lane);
         __syncwarp();
@@ -497,16 +570,20 @@ __global__ void __launch_bounds__(W8_WARPS * 32, 2) feat_warp8_kernel(const W8Pa
 #endif
 
 // ---- host side: table blob, support check, launch -------------------------------------------------
+inline int warp8_radix(const dspx_plan *pl) { return pl->P == 512 ? 4 : (pl->P == 1024 ? 8 : (pl->P == 2048 ? 16 : 0)); }
+
 inline bool warp8_supported(const dspx_plan *pl)
 {
-    return pl->P == 1024 && pl->cfg.frame_length == 1024 && (pl->cfg.hop_length % 2) == 0 &&
+    return warp8_radix(pl) != 0 && pl->cfg.frame_length == pl->P && (pl->cfg.hop_length % 2) == 0 &&
            pl->cfg.n_mels <= 256 && pl->cfg.n_mfcc <= 128 && pl->host.two_band_ok;
 }
 
 inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8Tables &tb)
 {
     const HostTables &h = pl->host;
-    const int n_mels = pl->cfg.n_mels, n_mfcc = pl->cfg.n_mfcc, n_bins = 513;
+    const int R1 = warp8_radix(pl), M = 64 * R1, P = 2 * M, J = 8 * R1;
+    const int n_mels = pl->cfg.n_mels, n_mfcc = pl->cfg.n_mfcc, n_bins = M + 1;
+    const int units = R1 >= 8 ? R1 / 8 : 1;
     // --- mel chunks from the bin view: runs of equal g, cut into chunks of 8 bins ---
     struct Chunk { int run, start, count; };
     std::vector<Chunk> chunks;
@@ -524,18 +601,19 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     const int n_chunks = (int)chunks.size();
     int rounds = std::max(1, (n_chunks + 31) / 32);
     if (rounds % 2 == 0) rounds++;                       // odd: lanes' 80-byte rows stay conflict-free
+    tb.r1 = R1;
     tb.rounds = rounds;
     tb.n_slots = 32 * rounds;
     tb.cw_lanes = n_mfcc <= 16 ? 16 : 32;
     const int dct_blocks = (n_mfcc + tb.cw_lanes - 1) / tb.cw_lanes;
-    tb.tile_floats = std::max(2048, 2 * (W8_CSTRIDE * tb.n_slots + 16)) + 16;
+    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16)) + 16;
     auto al4 = [](int x) { return (x + 3) & ~3; };
     int off = 0;
-    tb.win = off; off += 2 * 8 * 32 * 2;
-    tb.tw1 = off; off += 2 * 7 * 32 * 2;
+    tb.win = off; off += 2 * R1 * 32 * 2;
+    tb.tw1 = off; off += 2 * (R1 - 1) * 32 * 2;
     tb.tw2 = off; off += al4(7 * 8 * 2);
-    tb.ptw = off; off += 9 * 32 * 2;
-    tb.ppos = off; off += 9 * 32 * 2;
+    tb.ptw = off; off += units * 9 * 32 * 2;
+    tb.ppos = off; off += units * 9 * 32 * 2;
     tb.cw = off; off += tb.n_slots * W8_WROW;
     tb.cflag = off; off += tb.n_slots;
     tb.fdesc = off; off += n_mels * 4;
@@ -544,18 +622,18 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     blob.assign(tb.total, 0.f);
     const double two_pi = 2.0 * M_PI;
     for (int s = 0; s < 2; s++)
-        for (int a = 0; a < 8; a++)
+        for (int a = 0; a < R1; a++)
             for (int l = 0; l < 32; l++) {
                 const int n = 128 * a + 2 * (l + 32 * s);
-                blob[tb.win + ((s * 8 + a) * 32 + l) * 2] = (float)(0.5 * h.window[n]);
-                blob[tb.win + ((s * 8 + a) * 32 + l) * 2 + 1] = (float)(0.5 * h.window[n + 1]);
+                blob[tb.win + ((s * R1 + a) * 32 + l) * 2] = (float)(0.5 * h.window[n]);
+                blob[tb.win + ((s * R1 + a) * 32 + l) * 2 + 1] = (float)(0.5 * h.window[n + 1]);
             }
     for (int s = 0; s < 2; s++)
-        for (int ka = 1; ka < 8; ka++)
+        for (int ka = 1; ka < R1; ka++)
             for (int l = 0; l < 32; l++) {
-                const double ang = -two_pi * (double)((l + 32 * s) * ka) / 512.0;
-                blob[tb.tw1 + ((s * 7 + ka - 1) * 32 + l) * 2] = (float)std::cos(ang);
-                blob[tb.tw1 + ((s * 7 + ka - 1) * 32 + l) * 2 + 1] = (float)std::sin(ang);
+                const double ang = -two_pi * (double)((l + 32 * s) * ka) / (double)M;
+                blob[tb.tw1 + ((s * (R1 - 1) + ka - 1) * 32 + l) * 2] = (float)std::cos(ang);
+                blob[tb.tw1 + ((s * (R1 - 1) + ka - 1) * 32 + l) * 2 + 1] = (float)std::sin(ang);
             }
     for (int kb = 1; kb < 8; kb++)
         for (int c = 0; c < 8; c++) {
@@ -563,12 +641,13 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
             blob[tb.tw2 + ((kb - 1) * 8 + c) * 2] = (float)std::cos(ang);
             blob[tb.tw2 + ((kb - 1) * 8 + c) * 2 + 1] = (float)std::sin(ang);
         }
-    for (int m = 0; m < 9; m++)
-        for (int l = 0; l < 32; l++) {
-            const double ang = -two_pi * (double)w8_bin(l, m) / 1024.0;
-            blob[tb.ptw + (m * 32 + l) * 2] = (float)std::cos(ang);
-            blob[tb.ptw + (m * 32 + l) * 2 + 1] = (float)std::sin(ang);
-        }
+    for (int w = 0; w < units; w++)
+        for (int m = 0; m < 9; m++)
+            for (int l = 0; l < 32; l++) {
+                const double ang = -two_pi * (double)w8_bin(J, l + 32 * w, m) / (double)P;
+                blob[tb.ptw + ((w * 9 + m) * 32 + l) * 2] = (float)std::cos(ang);
+                blob[tb.ptw + ((w * 9 + m) * 32 + l) * 2 + 1] = (float)std::sin(ang);
+            }
     // chunk c lives at (lane = c / rounds, round = c % rounds); its bins sit at tile slots 10c .. 10c+7
     std::vector<int> pos(n_bins, W8_CSTRIDE * tb.n_slots + 8);          // dump slot for unused bins
     int32_t *cflag = reinterpret_cast<int32_t *>(blob.data() + tb.cflag);
@@ -590,12 +669,14 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         if (last) { seg_cnt[ch.run]++; seg++; }
     }
     int32_t *ppos = reinterpret_cast<int32_t *>(blob.data() + tb.ppos);
-    for (int m = 0; m < 9; m++)
-        for (int l = 0; l < 32; l++) {
-            const int k = w8_bin(l, m);
-            ppos[(m * 32 + l) * 2] = pos[k];
-            ppos[(m * 32 + l) * 2 + 1] = pos[512 - k];
-        }
+    for (int w = 0; w < units; w++)
+        for (int m = 0; m < 9; m++)
+            for (int l = 0; l < 32; l++) {
+                int k = w8_bin(J, l + 32 * w, m);
+                if (k > M) k = 0;                          // lanes without a unit (R1 = 4) never store
+                ppos[((w * 9 + m) * 32 + l) * 2] = pos[k];
+                ppos[((w * 9 + m) * 32 + l) * 2 + 1] = pos[M - k];
+            }
     int32_t *fdesc = reinterpret_cast<int32_t *>(blob.data() + tb.fdesc);
     for (int r = 0; r < n_runs; r++) {
         const int g = run_g[r];
@@ -637,7 +718,7 @@ inline int warp8_prepare(dspx_plan *pl)
     auto *pd = new W8PlanData();
     pd->tb = tb;
     pd->smem = smem;
-    pd->ctas_per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+    pd->ctas_per_sm = (tb.r1 != 16 && smem * 2 + 2048 <= 227 * 1024) ? 2 : 1;
     pl->fast_host = pd;
     DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));
     DSPX_CUDA_CHECK(cudaMemcpy(pl->d_fast_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -653,6 +734,20 @@ inline void warp8_release(dspx_plan *pl)
 
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                             int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
+
+template <int R1, bool PRE>
+inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, int64_t ctas, cudaStream_t st)
+{
+    // the opt-in shared-memory limit is a per-function attribute shared by all plans: only ever raise it
+    static size_t smem_set[64] = {};
+    if (pd->smem > smem_set[device & 63]) {
+        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
+        smem_set[device & 63] = pd->smem;
+    }
+    feat_warp8_kernel<R1, PRE><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
+    DSPX_CUDA_CHECK(cudaGetLastError());
+    return DSPX_OK;
+}
 
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                         int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw = 0)
@@ -683,19 +778,14 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
     const int64_t resident = (int64_t)pl->sm_count * pd->ctas_per_sm;
     if (ctas > resident) ctas = resident;                    // persistent: warps stride over the items
-    // the opt-in shared-memory limit is a per-function attribute shared by all plans: only ever raise it
-    static size_t smem_set_dev[64][2] = {};
     const bool pre = pl->cfg.pre_emphasis > 0.0;
-    size_t *smem_set = smem_set_dev[pl->device & 63];
-    if (pd->smem > smem_set[pre]) {
-        if (pre) DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
-        else DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
-        smem_set[pre] = pd->smem;
+    switch (pd->tb.r1) {
+        case 4: return pre ? w8_launch_one<4, true>(p, pd, pl->device, ctas, st) : w8_launch_one<4, false>(p, pd, pl->device, ctas, st);
+        case 8: return pre ? w8_launch_one<8, true>(p, pd, pl->device, ctas, st) : w8_launch_one<8, false>(p, pd, pl->device, ctas, st);
+        case 16: return pre ? w8_launch_one<16, true>(p, pd, pl->device, ctas, st) : w8_launch_one<16, false>(p, pd, pl->device, ctas, st);
     }
-    if (pre) feat_warp8_kernel<true><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
-    else feat_warp8_kernel<false><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
-    DSPX_CUDA_CHECK(cudaGetLastError());
-    return DSPX_OK;
+    set_error("warp8: bad radix");
+    return DSPX_EUNSUPPORTED;
 }
 #endif
 

@@ -52,7 +52,7 @@ extern "C" {
 /* kernel selection for dspx_features (dspx_plan_info.kernel reports the pick) */
 #define DSPX_KERNEL_AUTO 0
 #define DSPX_KERNEL_GENERIC 1  /* any power-of-two n_fft in [16, 8192] */
-#define DSPX_KERNEL_WARP8 2    /* warp-autonomous radix-8 f32x2 kernel, n_fft 512/1024/2048 */
+#define DSPX_KERNEL_WARP8 2    /* warp-autonomous packed-f32x2 kernel: frame_length = n_fft in {512, 1024, 2048} */
 
 /* Field-for-field image of the reference MfccConfig dataclass, src/dsp/mfcc.py:10-21. */
 typedef struct dspx_config {

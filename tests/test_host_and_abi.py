@@ -147,7 +147,7 @@ def test_generic_kernel_replay_matches_reference(built, golden_small):
 
 
 def test_warp8_kernel_replay_matches_reference(built, golden_small):
-    """feat_warp8.cuh lane-phase functions (radix-8 f32x2 kernel) replayed on the CPU."""
+    """feat_warp8.cuh lane-phase functions (f32x2 kernel, n_fft 512 / 1024 / 2048) replayed on the CPU."""
     lib, DspxConfig = _emu(built)
     z, meta = golden_small
     clips = np.ascontiguousarray(z["clips"])
@@ -160,7 +160,7 @@ def test_warp8_kernel_replay_matches_reference(built, golden_small):
         mf = np.zeros((3, t, m["n_mfcc"]), np.float32)
         rc = lib.emu_features_warp8(C.byref(cfg), fp(clips), C.c_int64(3), C.c_int64(clips.shape[1]),
                                     C.c_int64(clips.shape[1]), fp(lm), fp(mf))
-        supported = m["frame_length"] == 1024 and (m["n_fft"] in (None, 1024))
+        supported = m["frame_length"] in (512, 1024, 2048) and m["n_fft"] in (None, m["frame_length"])
         assert (rc == 0) == supported, (ci, rc)
         if rc != 0:
             continue
@@ -168,7 +168,7 @@ def test_warp8_kernel_replay_matches_reference(built, golden_small):
         for b in range(3):
             assert rel_err(mf[b], z[f"c{ci}_mfcc_{b}"]) < 1e-5, (ci, b)
             assert rel_err(lm[b], z[f"c{ci}_logmel_{b}"]) < 1e-5, (ci, b)
-    assert covered >= 8
+    assert covered >= 15
 
 
 def test_warp8_replay_full_clip(built, golden_config1):
