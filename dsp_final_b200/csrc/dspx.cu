@@ -732,10 +732,16 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     tp.n_splits = (int)((ndb + rps - 1) / rps);
     tp.idx_out = tp.n_splits == 1 ? idx_out_dev : pidx;
     tp.score_out = tp.n_splits == 1 ? score_out_dev : pscore;
-    const size_t smem = (size_t)(TK_ROWS + TK_QPC) * TK_DS * 8 + (size_t)TK_QPC * k * 12;
-    DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((nq + TK_QPC - 1) / TK_QPC), (unsigned)tp.n_splits);
-    cosine_topk_kernel<<<grid, TK_WARPS * 32, smem, st>>>(tp);
+    if (dim == 26) {                                   // MFCC embeddings: 2 x 13, the whole vector in one chunk
+        const size_t smem = topk_smem_bytes(dim, k, 26);
+        DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cosine_topk_kernel<26><<<grid, TK_WARPS * 32, smem, st>>>(tp);
+    } else {
+        const size_t smem = topk_smem_bytes(dim, k, 32);
+        DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cosine_topk_kernel<32><<<grid, TK_WARPS * 32, smem, st>>>(tp);
+    }
     DSPX_CUDA_CHECK(cudaGetLastError());
     if (tp.n_splits > 1) {
         topk_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(pidx, pscore, nq, tp.n_splits, k, idx_out_dev, score_out_dev);

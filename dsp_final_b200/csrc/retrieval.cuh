@@ -23,8 +23,6 @@ constexpr int TK_QPW = 8;                        // queries per warp
 constexpr int TK_QPC = TK_WARPS * TK_QPW;        // queries per CTA (64)
 constexpr int TK_RPL = 4;                        // database rows per lane and tile
 constexpr int TK_ROWS = 32 * TK_RPL;             // database rows per tile (128)
-constexpr int TK_DC = 32;                        // dimension chunk held in shared memory
-constexpr int TK_DS = TK_DC + 1;                 // odd row stride: conflict-free column reads
 constexpr int TK_MAX_SPLITS = 32;
 
 #if defined(__CUDACC__)
@@ -125,12 +123,69 @@ __device__ __forceinline__ void topk_warp_insert(double *ls, int32_t *li, int k,
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(TK_WARPS * 32) cosine_topk_kernel(const TopkParams p)
+// Slow path of the selection, kept out of line (the fast path is one vote per query and tile):
+// offer the four scores this lane holds for one query, rows tile + 32 r + lane, in ascending row order.
+struct TopkState {
+    double thr;
+    int cnt;
+};
+
+__device__ __noinline__ TopkState topk_offer(double s0, double s1, double s2, double s3, int64_t tile, int64_t r_end,
+                                             double *ls, int32_t *li, int k, int cnt, double thr, int lane)
 {
+#pragma unroll 1
+    for (int r = 0; r < TK_RPL; r++) {
+        const double s = r == 0 ? s0 : (r == 1 ? s1 : (r == 2 ? s2 : s3));
+        const int64_t gr = tile + 32 * r + lane;
+        const bool cand = (gr < r_end) && (cnt < k || s > thr);
+        unsigned mask = __ballot_sync(0xffffffffu, cand);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const double cs = __shfl_sync(0xffffffffu, s, src);
+            if (cnt == k && !(cs > thr)) continue;
+            topk_warp_insert(ls, li, k, cnt, cs, (int32_t)(tile + 32 * r + src), lane);
+            if (cnt == k) thr = ls[k - 1];
+        }
+    }
+    TopkState out;
+    out.thr = thr;
+    out.cnt = cnt;
+    return out;
+}
+
+// asynchronous global->shared copies; src_bytes = 0 zero-fills (rows / columns past the end)
+__device__ __forceinline__ void tk_cp_async16(double *dst, const double *src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n));
+}
+// asynchronous 8-byte global->shared copy; src_bytes = 0 zero-fills (rows / columns past the end)
+__device__ __forceinline__ void tk_cp_async8(double *dst, const double *src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n));
+}
+__device__ __forceinline__ void tk_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tk_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// CW = columns of the dimension chunk kept in shared memory (compile-time, even): 26 when the
+// whole MFCC embedding fits (2 x 13), 32 otherwise (last chunk zero-padded: fma(0, 0, acc) == acc).
+// A "stage" is one (database tile, dimension chunk) pair; stages are double-buffered with cp.async
+// so the next tile streams in while the current one is scored.
+template <int CW>
+__global__ void __launch_bounds__(TK_WARPS * 32, 2) cosine_topk_kernel(const TopkParams p)
+{
+    constexpr int DS = 34;                                             // even row stride (doubles): 16-byte aligned pairs,
+                                                                       // 272 B rows -> conflict-free 128-bit loads
     extern __shared__ __align__(16) unsigned char tk_raw[];
-    double *s_db = reinterpret_cast<double *>(tk_raw);                 // [TK_ROWS][TK_DS]
-    double *s_q = s_db + TK_ROWS * TK_DS;                              // [TK_QPC][TK_DS]
-    double *s_ls = s_q + TK_QPC * TK_DS;                               // [TK_QPC][k]
+    const int n_chunks = (p.dim + CW - 1) / CW;
+    const int q_bufs = n_chunks > 1 ? 2 : 1;
+    double *s_db = reinterpret_cast<double *>(tk_raw);                 // [2][TK_ROWS][DS]
+    double *s_q = s_db + 2 * TK_ROWS * DS;                             // [q_bufs][TK_QPC][DS]
+    double *s_ls = s_q + q_bufs * TK_QPC * DS;                         // [TK_QPC][k]
     int32_t *s_li = reinterpret_cast<int32_t *>(s_ls + (size_t)TK_QPC * p.k);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,74 +194,102 @@ __global__ void __launch_bounds__(TK_WARPS * 32) cosine_topk_kernel(const TopkPa
     const int64_t r_begin = (int64_t)split * p.rows_per_split;
     int64_t r_end = r_begin + p.rows_per_split;
     if (r_end > p.ndb) r_end = p.ndb;
-    const int n_chunks = (p.dim + TK_DC - 1) / TK_DC;
+    const int64_t n_tiles = (r_end - r_begin + TK_ROWS - 1) / TK_ROWS;
+    const int64_t n_stages = n_tiles * n_chunks;
+    const bool vec16 = (p.dim & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.dbn) | reinterpret_cast<uintptr_t>(p.qn)) & 15) == 0;
+
+    auto issue = [&](int64_t stage) {
+        const int64_t tile = r_begin + (stage / n_chunks) * TK_ROWS;
+        const int ch = (int)(stage % n_chunks), c0 = ch * CW, buf = (int)(stage & 1);
+        double *db = s_db + buf * TK_ROWS * DS;
+        double *qb = s_q + (n_chunks > 1 ? buf : 0) * TK_QPC * DS;
+        const bool load_q = n_chunks > 1 || stage == 0;
+        if (vec16) {                                   // even dim: every (row, even column) is 16-byte aligned
+            constexpr int CP = CW / 2;
+            for (int e = tid; e < TK_ROWS * CP; e += TK_WARPS * 32) {
+                const int row = e / CP, c = 2 * (e - row * CP);
+                const int64_t gr = tile + row;
+                const bool ok = gr < r_end && c0 + c < p.dim;
+                tk_cp_async16(db + row * DS + c, p.dbn + (ok ? (size_t)gr * p.dim + c0 + c : 0), ok);
+            }
+            if (load_q)
+                for (int e = tid; e < TK_QPC * CP; e += TK_WARPS * 32) {
+                    const int row = e / CP, c = 2 * (e - row * CP);
+                    const int64_t gq = q0 + row;
+                    const bool ok = gq < p.nq && c0 + c < p.dim;
+                    tk_cp_async16(qb + row * DS + c, p.qn + (ok ? (size_t)gq * p.dim + c0 + c : 0), ok);
+                }
+        } else {
+            for (int e = tid; e < TK_ROWS * CW; e += TK_WARPS * 32) {
+                const int row = e / CW, c = e - row * CW;
+                const int64_t gr = tile + row;
+                const bool ok = gr < r_end && c0 + c < p.dim;
+                tk_cp_async8(db + row * DS + c, p.dbn + (ok ? (size_t)gr * p.dim + c0 + c : 0), ok);
+            }
+            if (load_q)
+                for (int e = tid; e < TK_QPC * CW; e += TK_WARPS * 32) {
+                    const int row = e / CW, c = e - row * CW;
+                    const int64_t gq = q0 + row;
+                    const bool ok = gq < p.nq && c0 + c < p.dim;
+                    tk_cp_async8(qb + row * DS + c, p.qn + (ok ? (size_t)gq * p.dim + c0 + c : 0), ok);
+                }
+        }
+        tk_cp_commit();
+    };
 
     int cnt[TK_QPW];
     double thr[TK_QPW];
 #pragma unroll
     for (int qi = 0; qi < TK_QPW; qi++) { cnt[qi] = 0; thr[qi] = 0.0; }
+    double acc[TK_QPW][TK_RPL];
 
-    for (int64_t tile = r_begin; tile < r_end; tile += TK_ROWS) {
-        double acc[TK_QPW][TK_RPL];
+    if (n_stages > 0) issue(0);
+    for (int64_t stage = 0; stage < n_stages; stage++) {
+        const int ch = (int)(stage % n_chunks), buf = (int)(stage & 1);
+        const int64_t tile = r_begin + (stage / n_chunks) * TK_ROWS;
+        if (stage + 1 < n_stages) { issue(stage + 1); tk_cp_wait<1>(); }
+        else tk_cp_wait<0>();
+        __syncthreads();                                               // this stage's bytes are visible to all
+        if (ch == 0) {
 #pragma unroll
-        for (int qi = 0; qi < TK_QPW; qi++)
+            for (int qi = 0; qi < TK_QPW; qi++)
 #pragma unroll
-            for (int r = 0; r < TK_RPL; r++) acc[qi][r] = 0.0;
-
-        for (int ch = 0; ch < n_chunks; ch++) {
-            const int c0 = ch * TK_DC;
-            const int cw = (p.dim - c0) < TK_DC ? (p.dim - c0) : TK_DC;
-            __syncthreads();                                           // previous readers are done
-            for (int e = tid; e < TK_ROWS * cw; e += TK_WARPS * 32) {
-                const int row = e / cw, c = e - row * cw;
-                const int64_t gr = tile + row;
-                s_db[row * TK_DS + c] = gr < r_end ? p.dbn[(size_t)gr * p.dim + c0 + c] : 0.0;
-            }
-            if (n_chunks > 1 || tile == r_begin) {
-                for (int e = tid; e < TK_QPC * cw; e += TK_WARPS * 32) {
-                    const int row = e / cw, c = e - row * cw;
-                    const int64_t gq = q0 + row;
-                    s_q[row * TK_DS + c] = gq < p.nq ? p.qn[(size_t)gq * p.dim + c0 + c] : 0.0;
-                }
-            }
-            __syncthreads();
-            const double *qrow = s_q + (warp * TK_QPW) * TK_DS;
-            for (int c = 0; c < cw; c++) {
-                double dv[TK_RPL];
+                for (int r = 0; r < TK_RPL; r++) acc[qi][r] = 0.0;
+        }
+        const double *db = s_db + buf * TK_ROWS * DS + lane * DS;
+        const double *qrow = s_q + (n_chunks > 1 ? buf : 0) * TK_QPC * DS + (warp * TK_QPW) * DS;
 #pragma unroll
-                for (int r = 0; r < TK_RPL; r++) dv[r] = s_db[(lane + 32 * r) * TK_DS + c];
+        for (int cp = 0; cp < CW / 2; cp++) {
+            double2 dv[TK_RPL];
 #pragma unroll
-                for (int qi = 0; qi < TK_QPW; qi++) {
-                    const double qv = qrow[qi * TK_DS + c];
+            for (int r = 0; r < TK_RPL; r++) dv[r] = *reinterpret_cast<const double2 *>(db + 32 * r * DS + 2 * cp);
 #pragma unroll
-                    for (int r = 0; r < TK_RPL; r++) acc[qi][r] = fma(qv, dv[r], acc[qi][r]);
+            for (int qi = 0; qi < TK_QPW; qi++) {
+                const double2 qv = *reinterpret_cast<const double2 *>(qrow + qi * DS + 2 * cp);
+#pragma unroll
+                for (int r = 0; r < TK_RPL; r++) {
+                    acc[qi][r] = fma(qv.x, dv[r].x, acc[qi][r]);
+                    acc[qi][r] = fma(qv.y, dv[r].y, acc[qi][r]);
                 }
             }
         }
-
-        // selection: rows are visited in ascending index (r outer, lane inner)
+        if (ch == n_chunks - 1) {
+            // selection fast path: one vote per query and tile ("does any lane hold a score that beats the
+            // current k-th?"); rows past r_end score 0 and are filtered out in topk_offer
 #pragma unroll
-        for (int qi = 0; qi < TK_QPW; qi++) {
-            const int ql = warp * TK_QPW + qi;
-            if (q0 + ql >= p.nq) continue;                              // warp-uniform
-            double *ls = s_ls + (size_t)ql * p.k;
-            int32_t *li = s_li + (size_t)ql * p.k;
-#pragma unroll
-            for (int r = 0; r < TK_RPL; r++) {
-                const int64_t gr = tile + 32 * r + lane;
-                const double s = acc[qi][r];
-                const bool cand = (gr < r_end) && (cnt[qi] < p.k || s > thr[qi]);
-                unsigned mask = __ballot_sync(0xffffffffu, cand);
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const double cs = __shfl_sync(0xffffffffu, s, src);
-                    if (cnt[qi] == p.k && !(cs > thr[qi])) continue;
-                    topk_warp_insert(ls, li, p.k, cnt[qi], cs, (int32_t)(tile + 32 * r + src), lane);
-                    if (cnt[qi] == p.k) thr[qi] = ls[p.k - 1];
+            for (int qi = 0; qi < TK_QPW; qi++) {
+                const int ql = warp * TK_QPW + qi;
+                if (q0 + ql >= p.nq) continue;                          // warp-uniform
+                const double mx = fmax(fmax(acc[qi][0], acc[qi][1]), fmax(acc[qi][2], acc[qi][3]));
+                if (__any_sync(0xffffffffu, cnt[qi] < p.k || mx > thr[qi])) {
+                    const TopkState st = topk_offer(acc[qi][0], acc[qi][1], acc[qi][2], acc[qi][3], tile, r_end,
+                                                    s_ls + (size_t)ql * p.k, s_li + (size_t)ql * p.k, p.k, cnt[qi], thr[qi], lane);
+                    cnt[qi] = st.cnt;
+                    thr[qi] = st.thr;
                 }
             }
         }
+        __syncthreads();                                               // buffer `buf` may be refilled by stage + 2
     }
 
     // write this CTA's lists
@@ -224,6 +307,12 @@ __global__ void __launch_bounds__(TK_WARPS * 32) cosine_topk_kernel(const TopkPa
             if (p.score_out) p.score_out[o + e] = have ? ls[e] : -INFINITY;
         }
     }
+}
+
+inline size_t topk_smem_bytes(int dim, int k, int cw)
+{
+    const int n_chunks = (dim + cw - 1) / cw;
+    return (size_t)(2 * TK_ROWS + (n_chunks > 1 ? 2 : 1) * TK_QPC) * 34 * 8 + (size_t)TK_QPC * k * 12;
 }
 
 // merge the per-split sorted lists of one query (one warp per query, one list per lane)
