@@ -183,3 +183,25 @@ def test_warp8_replay_full_clip(built, golden_config1):
     fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
     assert lib.emu_features_warp8(C.byref(cfg), fp(x), C.c_int64(1), C.c_int64(220500), C.c_int64(220500), fp(lm), fp(mf)) == 0
     assert rel_err(mf[0], g["mfcc"]) < 1e-5 and rel_err(lm[0], g["logmel"]) < 1e-5
+
+
+def test_kernel_replay_is_addresssanitizer_clean(tmp_path):
+    """Out-of-bounds check of the kernels' index arithmetic: the CPU replay of both feature kernels
+    (exact-size shared-memory tiles and outputs) under AddressSanitizer, 11 configurations.
+    compute-sanitizer is closed on the GPU pool, so this is the memcheck we have."""
+    import shutil
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = tmp_path / "emu_asan"
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-g", "-std=c++17", "-Xcompiler",
+           "-fsanitize=address,-fno-omit-frame-pointer,-ffp-contract=off", "-o", str(exe),
+           str(REPO / "tests" / "replay_asan_main.cu"), str(REPO / "dsp_final_b200" / "csrc" / "emu.cu"), "-lasan"]
+    build = subprocess.run(cmd, capture_output=True, text=True)
+    if build.returncode != 0 and "asan" in (build.stderr + build.stdout).lower():
+        pytest.skip("libasan not available")
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True,
+                         env={"ASAN_OPTIONS": "protect_shadow_gap=0:detect_leaks=0", "PATH": "/usr/bin:/bin"})
+    assert run.returncode == 0 and "AddressSanitizer" not in run.stderr, run.stderr[-3000:]
+    lines = [l for l in run.stdout.splitlines() if l.startswith("fl ")]
+    assert len(lines) == 11 and all(l.endswith("finite 1") for l in lines)
