@@ -187,7 +187,7 @@ def log_mel_nchw(clips, cfg, device: int | None = None, kernel: str = "auto"):
 
 
 def stft_batch(clips, frame_length: int, hop_length: int, window: str = "hann", n_fft: int | None = None,
-               device: int | None = None, pre_emphasis: float = 0.0):
+               device: int | None = None, pre_emphasis: float = 0.0, kernel: str = "auto"):
     """[B, T, n_fft_pow2//2+1] complex64 STFT, src/dsp/stft.py:43-56 batched.
 
     pre_emphasis > 0 applies the MFCC path's filter first (the reference stft() has none).
@@ -203,7 +203,7 @@ def stft_batch(clips, frame_length: int, hop_length: int, window: str = "hann", 
         if x.dtype != torch.float32 or x.stride(1) != 1:
             x = x.to(torch.float32).contiguous()
         dev = x.device.index if device is None else device
-        plan = get_plan(cfg, dev, "generic")
+        plan = get_plan(cfg, dev, kernel)
         b, length = x.shape
         t = plan.num_frames(length)
         with torch.cuda.device(dev):
@@ -212,7 +212,7 @@ def stft_batch(clips, frame_length: int, hop_length: int, window: str = "hann", 
                                      torch.cuda.current_stream(dev).cuda_stream), "dspx_stft")
         return out
     x = _as_host_clips(clips)
-    plan = get_plan(cfg, device, "generic")
+    plan = get_plan(cfg, device, kernel)
     b, length = x.shape
     t = plan.num_frames(length)
     out = np.empty((b, t, plan.n_bins), np.complex64)

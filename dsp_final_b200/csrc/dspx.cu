@@ -196,6 +196,15 @@ static int features_device(const dspx_plan *pl, const float *clips, int64_t n_cl
     return rc;
 }
 
+// complex STFT: the warp8 kernel when frame_length == n_fft in {512, 1024, 2048} and the rows are aligned
+static int stft_device(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                       int64_t T, int pre, float2 *out, cudaStream_t st)
+{
+    if (pl->kernel == DSPX_KERNEL_WARP8 && pl->take_stft == pl->P && warp8_can_launch(clips, n_clips, clip_stride, T))
+        return launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, nullptr, nullptr, st, 0, out, pre);
+    return launch_generic(pl, clips, n_clips, clip_len, clip_stride, T, pl->take_stft, pre, nullptr, nullptr, out, st);
+}
+
 static int ensure_pipe(dspx_plan *pl, size_t in_bytes, size_t out_bytes, bool stage_in, bool stage_out, HostPipe **out,
                        size_t f32_bytes = 0)
 {
@@ -342,8 +351,7 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
         if (mode == 0)
             rc = features_device(pl, d_clips, cnt, clip_len, clip_len, d_lm, d_mf, d_em, st);
         else
-            rc = launch_generic(pl, d_clips, cnt, clip_len, clip_len, T, pl->take_stft, pre, nullptr, nullptr,
-                                reinterpret_cast<float2 *>(d_st), st);
+            rc = stft_device(pl, d_clips, cnt, clip_len, clip_len, T, pre, reinterpret_cast<float2 *>(d_st), st);
         if (rc != DSPX_OK) return rc;
         char *h_o = out_pinned ? nullptr : static_cast<char *>(hp->h_out[slot]);
         auto d2h = [&](float *user, size_t per, size_t off, const void *dsrc) -> int {
@@ -538,8 +546,8 @@ int dspx_stft(const dspx_plan *plan, const float *clips_dev, int64_t n_clips, in
     if (n_clips == 0) return DSPX_OK;
     DeviceGuard guard(plan->device);
     const int pre = (pre_emphasis && plan->cfg.pre_emphasis > 0.0) ? 1 : 0;
-    return launch_generic(plan, clips_dev, n_clips, clip_len, clip_stride, T, plan->take_stft, pre, nullptr, nullptr,
-                          reinterpret_cast<float2 *>(out_dev), static_cast<cudaStream_t>(stream));
+    return stft_device(plan, clips_dev, n_clips, clip_len, clip_stride, T, pre, reinterpret_cast<float2 *>(out_dev),
+                       static_cast<cudaStream_t>(stream));
 }
 
 int dspx_features(const dspx_plan *plan, const float *clips_dev, int64_t n_clips, int64_t clip_len, int64_t clip_stride,

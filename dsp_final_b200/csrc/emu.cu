@@ -141,7 +141,7 @@ int emu_features_generic(const dspx_config *cfg, const float *clips, int64_t n_c
 // Replays feat_warp8_kernel: one "warp" at a time, each phase run for lanes 0..31 in turn
 // (a __syncwarp() separates the phases on the device).
 int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_clips, int64_t clip_len,
-                       int64_t clip_stride, float *logmel, float *mfcc)
+                       int64_t clip_stride, float *logmel, float *mfcc, float *stft_out, int stft_pre)
 {
     EmuTables e;
     int rc = emu_build(cfg, e);
@@ -175,7 +175,8 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     p.mfcc = mfcc;
     p.lm_ts = p.n_mels;
     p.lm_fs = 1;
-    const bool pre = cfg->pre_emphasis > 0.0;
+    p.stft = reinterpret_cast<float2 *>(stft_out);
+    const bool pre = stft_out ? (stft_pre && cfg->pre_emphasis > 0.0) : (cfg->pre_emphasis > 0.0);
     std::vector<float> warp_smem(w8_warp_floats(tb, p.n_mels) + 4, 0.f);
     W8Ctx c;
     // 16-byte align the warp tile like the device carve-up does
@@ -201,6 +202,15 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
             if (r1 == 4) w8_pass2<4>(c, lane);
             else if (r1 == 8) w8_pass2<8>(c, lane);
             else w8_pass2<16>(c, lane);
+        }
+        if (p.stft) {
+            for (int lane = 0; lane < 32; lane++)
+                for (int w = 0; w < units; w++) {
+                    if (r1 == 4) w8_pass3_stft<4>(c, lane, w);
+                    else if (r1 == 8) w8_pass3_stft<8>(c, lane, w);
+                    else w8_pass3_stft<16>(c, lane, w);
+                }
+            continue;
         }
         for (int lane = 0; lane < 32; lane++)
             for (int w = 0; w < units; w++) {

@@ -189,6 +189,7 @@ struct W8Params {
     const float *tables;     // global copy of the blob
     float *logmel, *mfcc;    // either may be null
     int64_t lm_ts, lm_fs;    // log-mel strides between frames / filters ([B,T,M]: M,1; [B,1,M,T]: 1,T)
+    float2 *stft;            // STFT mode: complex spectrum [n_clips, n_frames, M + 1]
 };
 
 struct W8Ctx {               // everything one warp needs for one frame pair
@@ -206,6 +207,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     int n_mels, n_mfcc, rounds, cw_lanes, validB;
     float *logmelA, *logmelB, *mfccA, *mfccB;   // rows of the two frames (null when not requested)
     int64_t lm_fs;
+    float2 *stftA, *stftB;   // STFT mode: rows of the two frames
 };
 
 struct W8Power {             // |X|^2 of the bins one pass-3 unit owns, carried across the syncwarp
@@ -378,6 +380,65 @@ DSPX_HD void w8_pass3(const W8Ctx &c, int lane, int w, W8Power &pw)
     if (l0) w8_split(r2[3], i2[3], r2[4], i2[4], ptw[8 * 32], pw.lo[8], pw.hi[8]);
 }
 
+// ---- phase C': STFT mode -- same transforms and pairing, but the complex bins go straight to HBM ----
+// X[k] = E + T, X[M-k] = conj(E - T); consecutive lanes hold consecutive bins: coalesced 8-byte stores.
+DSPX_HD void w8_split_store(float2 ar, float2 ai, float2 br, float2 bi, float2 w, float2 *rowA, float2 *rowB,
+                            int k, int mk, bool validB)
+{
+    const float2 er = add2(ar, br), ei = sub2(ai, bi);
+    const float2 orr = add2(ai, bi), oi = sub2(br, ar);
+    const float2 wr = bc2(w.x), wi = bc2(w.y);
+    const float2 tr = fma2(neg2(oi), wi, mul2(orr, wr));
+    const float2 ti = fma2(orr, wi, mul2(oi, wr));
+    const float2 xr = add2(er, tr), xi = add2(ei, ti);
+    const float2 yr = sub2(er, tr), yi = sub2(ti, ei);
+    rowA[k] = make_float2(xr.x, xi.x);
+    rowA[mk] = make_float2(yr.x, yi.x);
+    if (validB) {
+        rowB[k] = make_float2(xr.y, xi.y);
+        rowB[mk] = make_float2(yr.y, yi.y);
+    }
+}
+
+template <int R1>
+DSPX_HD void w8_pass3_stft(const W8Ctx &c, int lane, int w)
+{
+    using G = W8Geo<R1>;
+    if (lane >= G::ACTIVE3) return;
+    const int u = lane + 32 * w;
+    const bool l0 = u == 0;
+    const int j1 = u, j2 = l0 ? G::J / 2 : G::J - u;
+    float2 r1[8], i1[8], r2[8], i2[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float4 v = c.xbuf[w8_addr(j1 & (R1 - 1), j1 >> G::LOG_R1, q)];
+        r1[q] = make_float2(v.x, v.y);
+        i1[q] = make_float2(v.z, v.w);
+        const float4 t = c.xbuf[w8_addr(j2 & (R1 - 1), j2 >> G::LOG_R1, q)];
+        r2[q] = make_float2(t.x, t.y);
+        i2[q] = make_float2(t.z, t.w);
+    }
+    dft8(r1, i1);
+    dft8(r2, i2);
+    const float2 *ptw = c.ptw + w * 9 * 32;
+    const bool vb = c.validB != 0;
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        float2 ar = r1[m], ai = i1[m];
+        if (m >= 5) { ar = sel2(l0, r2[m - 5], ar); ai = sel2(l0, i2[m - 5], ai); }
+        const int b0 = m == 0 ? 0 : (m <= 4 ? 8 - m : 0);
+        float2 br, bi;
+        if (m <= 4) { br = sel2(l0, r1[b0 & 7], r2[7 - m]); bi = sel2(l0, i1[b0 & 7], i2[7 - m]); }
+        else { br = sel2(l0, r2[12 - m], r2[7 - m]); bi = sel2(l0, i2[12 - m], i2[7 - m]); }
+        const int k = w8_bin(G::J, u, m);
+        w8_split_store(ar, ai, br, bi, ptw[m * 32 + lane], c.stftA, c.stftB, k, G::M - k, vb);
+    }
+    if (l0) {
+        const int k = w8_bin(G::J, 0, 8);
+        w8_split_store(r2[3], i2[3], r2[4], i2[4], ptw[8 * 32], c.stftA, c.stftB, k, G::M - k, vb);
+    }
+}
+
 // ---- phase D: power spectrum into the (re-used) tile, in mel-chunk order ---------------------------
 // ppos[w][m][lane] = tile slots of bins k_m and M - k_m: bins of one mel chunk are contiguous,
 // chunks sit W8_CSTRIDE slots apart, bins no filter uses go to a dump slot.
@@ -499,6 +560,9 @@ DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
     c.lm_fs = p.lm_fs;
     c.mfccA = p.mfcc ? p.mfcc + rowA * p.n_mfcc : nullptr;
     c.mfccB = p.mfcc ? p.mfcc + rowB * p.n_mfcc : nullptr;
+    const int64_t n_bins = 64 * p.tb.r1 + 1;
+    c.stftA = p.stft ? p.stft + rowA * n_bins : nullptr;
+    c.stftB = c.stftA ? c.stftA + n_bins : nullptr;
 }
 
 // the whole per-item sequence; SYNC is __syncwarp() on the device and a no-op in the lane-loop replay
@@ -514,7 +578,7 @@ __device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, in
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-template <int R1, bool PRE>
+template <int R1, bool PRE, bool STFT>
 __global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_kernel(const W8Params p)
 {
     using G = W8Geo<R1>;
@@ -546,6 +610,12 @@ __global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_ke
         __syncwarp();
         w8_pass2<R1>(c, lane);
         __syncwarp();
+        if (STFT) {
+#pragma unroll
+            for (int w = 0; w < G::UNITS; w++) w8_pass3_stft<R1>(c, lane, w);
+            __syncwarp();                   // the tile is rewritten by the next item's first pass
+            continue;
+        }
         W8Power pw[G::UNITS];
 #pragma unroll
         for (int w = 0; w < G::UNITS; w++) w8_pass3<R1>(c, lane, w, pw[w]);
@@ -735,27 +805,35 @@ inline void warp8_release(dspx_plan *pl)
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                             int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
 
-template <int R1, bool PRE>
+template <int R1, bool PRE, bool STFT>
 inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, int64_t ctas, cudaStream_t st)
 {
     // the opt-in shared-memory limit is a per-function attribute shared by all plans: only ever raise it
     static size_t smem_set[64] = {};
     if (pd->smem > smem_set[device & 63]) {
-        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
+        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE, STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
         smem_set[device & 63] = pd->smem;
     }
-    feat_warp8_kernel<R1, PRE><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
+    feat_warp8_kernel<R1, PRE, STFT><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
 }
 
+// 8-byte vector loads need even row strides and an 8-byte aligned base; items are 32-bit
+inline bool warp8_can_launch(const float *clips, int64_t n_clips, int64_t clip_stride, int64_t T)
+{
+    return !(clip_stride & 1) && !(reinterpret_cast<uintptr_t>(clips) & 7) && n_clips * ((T + 1) / 2) < (int64_t)0x7fffffff;
+}
+
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
-                        int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw = 0)
+                        int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw = 0,
+                        float2 *stft = nullptr, int stft_pre = 0)
 {
     const int64_t pairs = (T + 1) / 2;
-    // 8-byte vector loads need even row strides and an 8-byte aligned base; items are 32-bit
-    if ((clip_stride & 1) || (reinterpret_cast<uintptr_t>(clips) & 7) || n_clips * pairs >= (int64_t)0x7fffffff)
+    if (!warp8_can_launch(clips, n_clips, clip_stride, T)) {
+        if (stft) { set_error("warp8 stft: unaligned clips"); return DSPX_EUNSUPPORTED; }
         return launch_generic_fallback(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
+    }
     const W8PlanData *pd = static_cast<const W8PlanData *>(pl->fast_host);
     W8Params p{};
     p.clips = clips;
@@ -775,14 +853,23 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.mfcc = mfcc;
     p.lm_ts = nchw ? 1 : p.n_mels;
     p.lm_fs = nchw ? T : 1;
+    p.stft = stft;
     int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
     const int64_t resident = (int64_t)pl->sm_count * pd->ctas_per_sm;
     if (ctas > resident) ctas = resident;                    // persistent: warps stride over the items
+    if (stft) {
+        const bool pre = stft_pre && pl->cfg.pre_emphasis > 0.0;
+        switch (pd->tb.r1) {
+            case 4: return pre ? w8_launch_one<4, true, true>(p, pd, pl->device, ctas, st) : w8_launch_one<4, false, true>(p, pd, pl->device, ctas, st);
+            case 8: return pre ? w8_launch_one<8, true, true>(p, pd, pl->device, ctas, st) : w8_launch_one<8, false, true>(p, pd, pl->device, ctas, st);
+            case 16: return pre ? w8_launch_one<16, true, true>(p, pd, pl->device, ctas, st) : w8_launch_one<16, false, true>(p, pd, pl->device, ctas, st);
+        }
+    }
     const bool pre = pl->cfg.pre_emphasis > 0.0;
     switch (pd->tb.r1) {
-        case 4: return pre ? w8_launch_one<4, true>(p, pd, pl->device, ctas, st) : w8_launch_one<4, false>(p, pd, pl->device, ctas, st);
-        case 8: return pre ? w8_launch_one<8, true>(p, pd, pl->device, ctas, st) : w8_launch_one<8, false>(p, pd, pl->device, ctas, st);
-        case 16: return pre ? w8_launch_one<16, true>(p, pd, pl->device, ctas, st) : w8_launch_one<16, false>(p, pd, pl->device, ctas, st);
+        case 4: return pre ? w8_launch_one<4, true, false>(p, pd, pl->device, ctas, st) : w8_launch_one<4, false, false>(p, pd, pl->device, ctas, st);
+        case 8: return pre ? w8_launch_one<8, true, false>(p, pd, pl->device, ctas, st) : w8_launch_one<8, false, false>(p, pd, pl->device, ctas, st);
+        case 16: return pre ? w8_launch_one<16, true, false>(p, pd, pl->device, ctas, st) : w8_launch_one<16, false, false>(p, pd, pl->device, ctas, st);
     }
     set_error("warp8: bad radix");
     return DSPX_EUNSUPPORTED;

@@ -159,7 +159,7 @@ def test_warp8_kernel_replay_matches_reference(built, golden_small):
         lm = np.zeros((3, t, m["n_mels"]), np.float32)
         mf = np.zeros((3, t, m["n_mfcc"]), np.float32)
         rc = lib.emu_features_warp8(C.byref(cfg), fp(clips), C.c_int64(3), C.c_int64(clips.shape[1]),
-                                    C.c_int64(clips.shape[1]), fp(lm), fp(mf))
+                                    C.c_int64(clips.shape[1]), fp(lm), fp(mf), None, 0)
         supported = m["frame_length"] in (512, 1024, 2048) and m["n_fft"] in (None, m["frame_length"])
         assert (rc == 0) == supported, (ci, rc)
         if rc != 0:
@@ -181,7 +181,7 @@ def test_warp8_replay_full_clip(built, golden_config1):
     lm = np.zeros((1, 429, 40), np.float32)
     mf = np.zeros((1, 429, 13), np.float32)
     fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
-    assert lib.emu_features_warp8(C.byref(cfg), fp(x), C.c_int64(1), C.c_int64(220500), C.c_int64(220500), fp(lm), fp(mf)) == 0
+    assert lib.emu_features_warp8(C.byref(cfg), fp(x), C.c_int64(1), C.c_int64(220500), C.c_int64(220500), fp(lm), fp(mf), None, 0) == 0
     assert rel_err(mf[0], g["mfcc"]) < 1e-5 and rel_err(lm[0], g["logmel"]) < 1e-5
 
 
