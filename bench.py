@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--outputs", default="mfcc+log_mel", choices=("mfcc", "log_mel", "mfcc+log_mel"))
     ap.add_argument("--kernel", default="auto", choices=("auto", "generic", "warp8"))
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--stft-steps", type=int, default=10, help="secondary stft() measurement (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -257,6 +258,34 @@ def run_ours(args) -> None:
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                 "note": "co-bound by FP32 issue + shared-memory bandwidth (DESIGN.md): 2.67 MFLOP per audio-second"}
 
+    # secondary: the stft() entry point on the same clips (complex64 [B, 429, 513] out: write-heavy, HBM-bound)
+    stft_info = None
+    if args.stft_steps > 0:
+        from dsp_final_b200.batch import stft_batch
+
+        s_out = stft_batch(clips, FL, HOP)
+        for _ in range(2):
+            stft_batch(clips, FL, HOP)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.stft_steps):
+            s_out = stft_batch(clips, FL, HOP)
+        s1.record(stream)
+        barrier()
+        st_ms = s0.elapsed_time(s1) / args.stft_steps
+        tt = torch.tensor([st_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        st_ms = float(tt.item())
+        st_bytes = b * (4 * CLIP_LEN + 8 * n_frames * (FL // 2 + 1))
+        stft_info = {"value": world * b * CLIP_SECONDS / (st_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": st_ms,
+                     "roofline": {"bound": "hbm", "achieved": st_bytes / (st_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": st_bytes / (st_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": st_bytes},
+                     "kernel": "feat_warp8 (STFT mode)", "steps": args.stft_steps}
+        stft_sel = s_out[[0, b - 1]][:, [0, 1, n_frames - 1]].cpu().numpy()
+        del s_out
+
     # end to end through the host-buffer C ABI: pinned host clips in, host features out
     e2e = None
     if args.e2e_steps > 0:
@@ -333,6 +362,9 @@ def run_ours(args) -> None:
     if lm is not None:
         parity["log_mel_rel_err"] = O.relative_error(lm[sel].cpu().numpy(), ref["log_mel"])
     parity["clips_checked"] = len(sel)
+    if stft_info is not None:
+        ref_st = np.stack([O.stft(clips[i].cpu().numpy(), FL, HOP)[[0, 1, n_frames - 1]] for i in (0, b - 1)])
+        parity["stft_rel_err"] = O.relative_error(stft_sel, ref_st)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
@@ -357,7 +389,7 @@ def run_ours(args) -> None:
                                f"{N_MELS} mels, {N_MFCC} MFCC (BASELINE.json configs[1])",
                    "outputs": args.outputs, "clips_per_gpu": b, "kernel": plan.kernel,
                    "l2_policy": "inputs_larger_than_l2 (1.76 GB per pass vs 126 MB L2)", "parallelism": f"clip-sharded x{world}"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps, "stft": stft_info,
         "clocks": clocks, "parity": parity,
     }
     print(json.dumps(line), flush=True)
