@@ -194,9 +194,12 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     for (uint32_t item = 0; item < p.n_items; item++) {
         w8_set_item(p, c, item);
         for (int lane = 0; lane < 32; lane++) {
-            if (r1 == 4) { if (pre) w8_pass1<4, true>(c, lane); else w8_pass1<4, false>(c, lane); }
-            else if (r1 == 8) { if (pre) w8_pass1<8, true>(c, lane); else w8_pass1<8, false>(c, lane); }
-            else { if (pre) w8_pass1<16, true>(c, lane); else w8_pass1<16, false>(c, lane); }
+            const bool share = 2 * cfg->hop_length == e.P && r1 != 16;
+            if (r1 == 4 && share) { if (pre) w8_pass1<4, true, true>(c, lane); else w8_pass1<4, false, true>(c, lane); }
+            else if (r1 == 4) { if (pre) w8_pass1<4, true, false>(c, lane); else w8_pass1<4, false, false>(c, lane); }
+            else if (r1 == 8 && share) { if (pre) w8_pass1<8, true, true>(c, lane); else w8_pass1<8, false, true>(c, lane); }
+            else if (r1 == 8) { if (pre) w8_pass1<8, true, false>(c, lane); else w8_pass1<8, false, false>(c, lane); }
+            else { if (pre) w8_pass1<16, true, false>(c, lane); else w8_pass1<16, false, false>(c, lane); }
         }
         for (int lane = 0; lane < 32; lane++) {
             if (r1 == 4) w8_pass2<4>(c, lane);

@@ -27,6 +27,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "dspx_internal.cuh"
 
@@ -159,7 +160,9 @@ DSPX_HD void dftn(float2 (&re)[16], float2 (&im)[16]) { dft16(re, im); }
 DSPX_HD int w8_addr(int ka, int x, int c) { return ((ka * 8 + x) << 3) | (c ^ (ka & 7)); }
 
 constexpr int W8_CHUNK = 8;               // bins per mel chunk
-constexpr int W8_CSTRIDE = 10;            // float2 slots per chunk in the power tile (80 B: conflict-free LDS.128)
+constexpr int W8_CSTRIDE = 8;             // float2 slots per chunk in the power tile: chunks are contiguous, so the
+                                          // scattered power stores of consecutive bins stay conflict-free; the reads
+                                          // are de-conflicted by a per-lane rotation (w8_mel_chunks)
 constexpr int W8_WROW = 20;               // floats per chunk row of the weight table (a0 b0 .. a7 b7 + pad)
 
 // Geometry for first-pass radix R1: M = 64 R1 complex points (n_fft = 128 R1), J = 8 R1 output residues.
@@ -183,7 +186,7 @@ struct W8Params {
     const float *clips;
     int64_t n_clips, clip_stride, n_frames;
     uint32_t pairs_per_clip, n_items;
-    int hop, n_mels, n_mfcc, prefetch;
+    int hop, n_mels, n_mfcc, prefetch, share;
     float alpha;
     W8Tables tb;
     const float *tables;     // global copy of the blob
@@ -241,9 +244,62 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
 // ---- phase A: load, pre-emphasis, window, radix-R1 over a, twiddle, store -----------------
 // All loads of a set are issued before the first use (memory-level parallelism); the only
 // sample without a predecessor is sample 0 of a clip (y[0] = x[0], src/dsp/mfcc.py:88).
-template <int R1, bool PRE>
+template <int R1, bool PRE, bool SHARE>
 DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 {
+    if (SHARE) {
+        // hop == n_fft / 2: frame B's rows 0..R1/2-1 are frame A's rows R1/2..R1-1.  Load the 3/2 R1
+        // distinct rows once, pre-emphasise them once (scalar), and pair them up for the two frames.
+        constexpr int SH = R1 / 2, NR = R1 + SH;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int tid = lane + 32 * s;
+            const float *pa = c.fa + 2 * tid;
+            float2 x[NR];
+            float pv[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                const int rr = (r >= R1 && !c.validB) ? r - SH : r;      // no frame B: replay frame A's rows
+                x[r] = *reinterpret_cast<const float2 *>(pa + 128 * rr);
+            }
+            if (PRE) {
+                const bool edge = c.firstA && tid == 0;
+                pv[0] = *(edge ? pa : pa - 1);
+                if (edge) pv[0] = 0.f;
+#pragma unroll
+                for (int r = 1; r < NR; r++) {
+                    const int rr = (r >= R1 && !c.validB) ? r - SH : r;
+                    pv[r] = pa[128 * rr - 1];
+                }
+            }
+            float y0[NR], y1[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                y0[r] = x[r].x;
+                y1[r] = x[r].y;
+                if (PRE) {
+                    y1[r] = DSPX_FSUB_RN(x[r].y, DSPX_FMUL_RN(c.alpha, x[r].x));
+                    y0[r] = DSPX_FSUB_RN(x[r].x, DSPX_FMUL_RN(c.alpha, pv[r]));
+                }
+            }
+            float2 re[R1], im[R1];
+#pragma unroll
+            for (int a = 0; a < R1; a++) {
+                const float2 w = c.win[(s * R1 + a) * 32 + lane];       // (0.5 w[n], 0.5 w[n+1])
+                re[a] = mul2(make_float2(y0[a], y0[a + SH]), bc2(w.x));
+                im[a] = mul2(make_float2(y1[a], y1[a + SH]), bc2(w.y));
+            }
+            dftn(re, im);
+            c.xbuf[w8_addr(0, tid >> 3, tid & 7)] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
+#pragma unroll
+            for (int ka = 1; ka < R1; ka++) {
+                const float2 w = c.tw1[(s * (R1 - 1) + ka - 1) * 32 + lane];
+                cmul2(re[ka], im[ka], w.x, w.y);
+                c.xbuf[w8_addr(ka, tid >> 3, tid & 7)] = make_float4(re[ka].x, re[ka].y, im[ka].x, im[ka].y);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         const int tid = lane + 32 * s;
@@ -297,6 +353,9 @@ template <int R1>
 DSPX_HD void w8_pass2(const W8Ctx &c, int lane)
 {
     const int cc = lane & 7;
+    float2 tw[7];                                   // exp(-2 pi i c k_b / 64): the same for every set of this lane
+#pragma unroll
+    for (int kb = 1; kb < 8; kb++) tw[kb - 1] = c.tw2[(kb - 1) * 8 + cc];
 #pragma unroll
     for (int s = 0; s < W8Geo<R1>::SETS2; s++) {
         const int ka = (lane >> 3) + 4 * s;
@@ -311,8 +370,7 @@ DSPX_HD void w8_pass2(const W8Ctx &c, int lane)
         c.xbuf[w8_addr(ka, 0, cc)] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
 #pragma unroll
         for (int kb = 1; kb < 8; kb++) {
-            const float2 w = c.tw2[(kb - 1) * 8 + cc];
-            cmul2(re[kb], im[kb], w.x, w.y);
+            cmul2(re[kb], im[kb], tw[kb - 1].x, tw[kb - 1].y);
             c.xbuf[w8_addr(ka, kb, cc)] = make_float4(re[kb].x, re[kb].y, im[kb].x, im[kb].y);
         }
     }
@@ -464,8 +522,10 @@ DSPX_HD void w8_store_power(const W8Ctx &c, int lane, int w, const W8Power &pw)
 // Every bin k feeds (at most) filter g(k) with weight a_k and filter g(k)+1 with weight b_k
 // (csrc/tables.cuh "bin view").  Runs of equal g are cut into chunks of 8 bins; lane l walks
 // chunks l*R .. l*R+R-1, accumulating in registers while the run continues and dropping one
-// (sum a P, sum b P) segment per run piece.  P and weight rows are 80 bytes apart: the
-// 128-bit loads of 8 neighbouring lanes hit 8 different bank groups.
+// (sum a P, sum b P) segment per run piece.  Chunks are 64 B apart in the tile, so chunk parity picks
+// the half of a 128-byte line and the lane reads its four 16-byte pieces rotated by (lane >> 1) & 3:
+// the 128-bit loads of 8 neighbouring lanes hit 8 different bank groups (rounds is odd, so parity
+// alternates with the lane).  The weight rows (80 B apart) are stored pre-rotated to match.
 DSPX_HD void w8_mel_chunks(const W8Ctx &c, int lane)
 {
     float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
@@ -475,9 +535,10 @@ DSPX_HD void w8_mel_chunks(const W8Ctx &c, int lane)
         const float4 *pp = reinterpret_cast<const float4 *>(c.pbuf + ch * W8_CSTRIDE);
         const float4 *ww = reinterpret_cast<const float4 *>(c.cw + ch * W8_WROW);
         float2 ca = make_float2(0.f, 0.f), cb = make_float2(0.f, 0.f);
+        const int rot = (lane >> 1) & 3;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const float4 p = pp[q], w = ww[q];                          // (P0A P0B P1A P1B), (a0 b0 a1 b1)
+            const float4 p = pp[(q + rot) & 3], w = ww[q];              // (P0A P0B P1A P1B), (a0 b0 a1 b1)
             ca = fma2(make_float2(p.x, p.y), bc2(w.x), ca);
             cb = fma2(make_float2(p.x, p.y), bc2(w.y), cb);
             ca = fma2(make_float2(p.z, p.w), bc2(w.z), ca);
@@ -578,7 +639,7 @@ __device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, in
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-template <int R1, bool PRE, bool STFT>
+template <int R1, bool PRE, bool STFT, bool SHARE>
 __global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_kernel(const W8Params p)
 {
     using G = W8Geo<R1>;
@@ -605,7 +666,7 @@ __global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_ke
     const uint32_t n_warps = gridDim.x * W8_WARPS;
     for (uint32_t item = blockIdx.x * W8_WARPS + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
-        w8_pass1<R1, PRE>(c, lane);
+        w8_pass1<R1, PRE, SHARE>(c, lane);
         if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
         w8_pass2<R1>(c, lane);
@@ -726,11 +787,13 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     int seg = 0;
     for (int ci = 0; ci < n_chunks; ci++) {
         const Chunk &ch = chunks[ci];
+        const int rot = ((ci / rounds) >> 1) & 3;          // rotation used by the lane that owns this chunk
         for (int j = 0; j < ch.count; j++) {
             const int k = ch.start + j;
             pos[k] = W8_CSTRIDE * ci + j;
-            blob[tb.cw + ci * W8_WROW + 2 * j] = h.bin_wfall[k];
-            blob[tb.cw + ci * W8_WROW + 2 * j + 1] = h.bin_wrise[k];
+            const int piece = (((j >> 1) - rot) & 3), jj = 2 * piece + (j & 1);      // where the lane meets bin j
+            blob[tb.cw + ci * W8_WROW + 2 * jj] = h.bin_wfall[k];
+            blob[tb.cw + ci * W8_WROW + 2 * jj + 1] = h.bin_wrise[k];
         }
         const bool first = (ci % rounds == 0) || chunks[ci - 1].run != ch.run;
         const bool last = (ci % rounds == rounds - 1) || ci == n_chunks - 1 || chunks[ci + 1].run != ch.run;
@@ -805,18 +868,27 @@ inline void warp8_release(dspx_plan *pl)
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                             int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
 
-template <int R1, bool PRE, bool STFT>
-inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, int64_t ctas, cudaStream_t st)
+template <int R1, bool PRE, bool STFT, bool SHARE>
+inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, int64_t ctas, cudaStream_t st)
 {
     // the opt-in shared-memory limit is a per-function attribute shared by all plans: only ever raise it
     static size_t smem_set[64] = {};
     if (pd->smem > smem_set[device & 63]) {
-        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE, STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
+        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE, STFT, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
         smem_set[device & 63] = pd->smem;
     }
-    feat_warp8_kernel<R1, PRE, STFT><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
+    feat_warp8_kernel<R1, PRE, STFT, SHARE><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
+}
+
+template <int R1, bool PRE, bool STFT>
+inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, int64_t ctas, cudaStream_t st)
+{
+    // rows are shared between the two frames of a pair when hop == n_fft / 2 (R1 = 16 keeps the plain loads:
+    // 24 distinct rows in flight would not fit its register budget)
+    if (R1 != 16 && p.share) return w8_launch_cfg<R1, PRE, STFT, (R1 != 16)>(p, pd, device, ctas, st);
+    return w8_launch_cfg<R1, PRE, STFT, false>(p, pd, device, ctas, st);
 }
 
 // 8-byte vector loads need even row strides and an 8-byte aligned base; items are 32-bit
@@ -846,6 +918,7 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.n_mels = pl->cfg.n_mels;
     p.n_mfcc = pl->cfg.n_mfcc;
     p.prefetch = 1;
+    p.share = (2 * pl->cfg.hop_length == pl->P) && !getenv("DSPX_W8_NOSHARE");
     p.alpha = (float)pl->cfg.pre_emphasis;
     p.tb = pd->tb;
     p.tables = static_cast<const float *>(pl->d_fast_tables);

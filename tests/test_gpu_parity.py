@@ -376,3 +376,38 @@ def test_retrieval_ml_dimensions(torch_cuda, dim):
     res = RM.evaluate_retrieval(items(tdb), items(tq), db, q, (10, 20))
     want = O.evaluate_retrieval(tdb, tq, db, q, (10, 20))
     assert [(r.k, r.precision) for r in res] == want
+
+
+@pytest.mark.parametrize("fl,hop", [(1024, 512), (512, 256), (2048, 512), (1024, 300)])
+def test_stft_full_size_properties(torch_cuda, fl, hop):
+    """stft() at ESC-50 clip length on the fast kernel: oracle parity on sampled frames plus
+    size-independent properties (linearity, Parseval per frame, DC / Nyquist bins are real)."""
+    torch = torch_cuda
+    from dsp_final_b200 import synth
+    from dsp_final_b200.batch import stft_batch
+    from dsp_final_b200.dsp.stft import _get_window
+    from oracle import oracle as O
+
+    x = torch.as_tensor(synth.host_clips(12, seed=21)).cuda()
+    y = torch.as_tensor(synth.host_clips(12, seed=22)).cuda()
+    sx, sy = stft_batch(x, fl, hop), stft_batch(y, fl, hop)
+    t = 1 + (220_500 - fl) // hop
+    assert sx.shape == (12, t, fl // 2 + 1) and sx.dtype == torch.complex64
+    sel = [0, 1, t // 2, t - 1]
+    ref = O.stft(x[3].cpu().numpy(), fl, hop)[sel]
+    _close(sx[3][sel].cpu().numpy(), ref, f"stft {fl}/{hop}")
+    # linearity: stft(2x - 0.5y) == 2 stft(x) - 0.5 stft(y)
+    lin = stft_batch(2.0 * x - 0.5 * y, fl, hop)
+    assert rel_err(lin.cpu().numpy(), (2.0 * sx - 0.5 * sy).cpu().numpy()) < 2e-6
+    # Parseval per frame: sum |frame * w|^2 = (|X0|^2 + |X_{N/2}|^2 + 2 sum_{0<k<N/2} |X_k|^2) / N
+    w = torch.as_tensor(_get_window("hann", fl).astype(np.float32)).cuda()
+    frames = x[0].unfold(0, fl, hop)[:t] * w
+    lhs = (frames.double() ** 2).sum(dim=1)
+    p = (sx[0].real.double() ** 2 + sx[0].imag.double() ** 2)
+    rhs = (p[:, 0] + p[:, -1] + 2.0 * p[:, 1:-1].sum(dim=1)) / fl
+    assert torch.allclose(lhs, rhs, rtol=1e-5, atol=1e-9)
+    assert float(sx[..., 0].imag.abs().max()) < 1e-4 * float(sx[..., 0].real.abs().max() + 1e-30) + 1e-6
+    assert float(sx[..., -1].imag.abs().max()) < 1e-4 * float(sx[..., -1].real.abs().max() + 1e-30) + 1e-6
+    # the generic kernel agrees with the fast one
+    g = stft_batch(x[:2], fl, hop, kernel="generic")
+    assert rel_err(g.cpu().numpy(), sx[:2].cpu().numpy()) < 1e-6
