@@ -33,7 +33,9 @@
 
 namespace dspx {
 
-constexpr int W8_WARPS = 8;               // warps per CTA
+constexpr int W8_WARPS = 8;               // warps per CTA, two CTAs per SM (128 registers per thread)
+constexpr int W8_WARPS_WIDE = 20;         // or one 20-warp CTA per SM (<= 102 registers): more warps in flight to
+                                          // cover the shared-memory pipe; +6 % on the feature path, worse for STFT mode
 
 
 
@@ -639,8 +641,8 @@ __device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, in
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-template <int R1, bool PRE, bool STFT, bool SHARE>
-__global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_kernel(const W8Params p)
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW>
+__global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_warp8_kernel(const W8Params p)
 {
     using G = W8Geo<R1>;
     extern __shared__ __align__(16) float w8_smem[];
@@ -651,9 +653,9 @@ __global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_ke
     {
         const float4 *src = reinterpret_cast<const float4 *>(p.tables);
         float4 *dst = reinterpret_cast<float4 *>(w8_smem);
-        for (int i = tid; i < p.tb.total / 4; i += W8_WARPS * 32) dst[i] = src[i];
+        for (int i = tid; i < p.tb.total / 4; i += NW * 32) dst[i] = src[i];
         float4 *z = reinterpret_cast<float4 *>(w8_smem + p.tb.total);
-        for (int i = tid; i < W8_WARPS * wf / 4; i += W8_WARPS * 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < NW * wf / 4; i += NW * 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     W8Ctx c;
@@ -663,8 +665,8 @@ __global__ void __launch_bounds__(W8_WARPS * 32, R1 == 16 ? 1 : 2) feat_warp8_ke
     c.n_mfcc = p.n_mfcc;
     c.rounds = p.tb.rounds;
     c.cw_lanes = p.tb.cw_lanes;
-    const uint32_t n_warps = gridDim.x * W8_WARPS;
-    for (uint32_t item = blockIdx.x * W8_WARPS + warp; item < p.n_items; item += n_warps) {
+    const uint32_t n_warps = gridDim.x * NW;
+    for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
         w8_pass1<R1, PRE, SHARE>(c, lane);
         if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
@@ -829,9 +831,9 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
             }
 }
 
-inline size_t warp8_smem_bytes(const W8Tables &tb, int n_mels)
+inline size_t warp8_smem_bytes(const W8Tables &tb, int n_mels, int n_warps = W8_WARPS)
 {
-    return ((size_t)tb.total + (size_t)W8_WARPS * w8_warp_floats(tb, n_mels)) * sizeof(float);
+    return ((size_t)tb.total + (size_t)n_warps * w8_warp_floats(tb, n_mels)) * sizeof(float);
 }
 
 #if defined(__CUDACC__)
@@ -839,6 +841,7 @@ struct W8PlanData {
     W8Tables tb;
     int ctas_per_sm;
     size_t smem;
+    size_t smem_wide;        // 0 when the 20-warp configuration does not fit
 };
 
 inline int warp8_prepare(dspx_plan *pl)
@@ -852,6 +855,8 @@ inline int warp8_prepare(dspx_plan *pl)
     pd->tb = tb;
     pd->smem = smem;
     pd->ctas_per_sm = (tb.r1 != 16 && smem * 2 + 2048 <= 227 * 1024) ? 2 : 1;
+    const size_t wide = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_WIDE);
+    pd->smem_wide = (tb.r1 != 16 && wide + 1024 <= 227 * 1024 && !getenv("DSPX_W8_NARROW")) ? wide : 0;
     pl->fast_host = pd;
     DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));
     DSPX_CUDA_CHECK(cudaMemcpy(pl->d_fast_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -868,27 +873,42 @@ inline void warp8_release(dspx_plan *pl)
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                             int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
 
-template <int R1, bool PRE, bool STFT, bool SHARE>
-inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, int64_t ctas, cudaStream_t st)
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW>
+inline int w8_launch_nw(const W8Params &p, size_t smem, int device, int64_t ctas, cudaStream_t st)
 {
     // the opt-in shared-memory limit is a per-function attribute shared by all plans: only ever raise it
     static size_t smem_set[64] = {};
-    if (pd->smem > smem_set[device & 63]) {
-        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE, STFT, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd->smem));
-        smem_set[device & 63] = pd->smem;
+    if (smem > smem_set[device & 63]) {
+        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[device & 63] = smem;
     }
-    feat_warp8_kernel<R1, PRE, STFT, SHARE><<<(unsigned)ctas, W8_WARPS * 32, pd->smem, st>>>(p);
+    feat_warp8_kernel<R1, PRE, STFT, SHARE, NW><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
 }
 
+template <int R1, bool PRE, bool STFT, bool SHARE>
+inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, int sm_count, cudaStream_t st)
+{
+    // persistent grid: warps stride over the items
+    if (!STFT && R1 != 16 && pd->smem_wide) {
+        int64_t ctas = ((int64_t)p.n_items + W8_WARPS_WIDE - 1) / W8_WARPS_WIDE;
+        if (ctas > sm_count) ctas = sm_count;
+        return w8_launch_nw<R1, PRE, STFT, SHARE, (R1 != 16 && !STFT) ? W8_WARPS_WIDE : W8_WARPS>(p, pd->smem_wide, device, ctas, st);
+    }
+    int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
+    const int64_t resident = (int64_t)sm_count * pd->ctas_per_sm;
+    if (ctas > resident) ctas = resident;
+    return w8_launch_nw<R1, PRE, STFT, SHARE, W8_WARPS>(p, pd->smem, device, ctas, st);
+}
+
 template <int R1, bool PRE, bool STFT>
-inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, int64_t ctas, cudaStream_t st)
+inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, int sm_count, cudaStream_t st)
 {
     // rows are shared between the two frames of a pair when hop == n_fft / 2 (R1 = 16 keeps the plain loads:
     // 24 distinct rows in flight would not fit its register budget)
-    if (R1 != 16 && p.share) return w8_launch_cfg<R1, PRE, STFT, (R1 != 16)>(p, pd, device, ctas, st);
-    return w8_launch_cfg<R1, PRE, STFT, false>(p, pd, device, ctas, st);
+    if (R1 != 16 && p.share) return w8_launch_cfg<R1, PRE, STFT, (R1 != 16)>(p, pd, device, sm_count, st);
+    return w8_launch_cfg<R1, PRE, STFT, false>(p, pd, device, sm_count, st);
 }
 
 // 8-byte vector loads need even row strides and an 8-byte aligned base; items are 32-bit
@@ -927,9 +947,7 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.lm_ts = nchw ? 1 : p.n_mels;
     p.lm_fs = nchw ? T : 1;
     p.stft = stft;
-    int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
-    const int64_t resident = (int64_t)pl->sm_count * pd->ctas_per_sm;
-    if (ctas > resident) ctas = resident;                    // persistent: warps stride over the items
+    const int ctas = pl->sm_count;                           // grid size is derived per configuration in w8_launch_cfg
     if (stft) {
         const bool pre = stft_pre && pl->cfg.pre_emphasis > 0.0;
         switch (pd->tb.r1) {
