@@ -40,7 +40,7 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     OUT.mkdir(exist_ok=True)
     lib = OUT / "libdspx.so"
     if force or _stale(lib):
-        cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+        cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "128", "-Xcompiler", "-fPIC", "-shared",
                "-o", str(lib), str(CSRC / "dspx.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -52,7 +52,7 @@ def build_emu(force: bool = False) -> Path:
     OUT.mkdir(exist_ok=True)
     lib = OUT / "libdspx_emu.so"
     if force or _stale(lib):
-        cmd = [_nvcc(), *ARCH, "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
+        cmd = [_nvcc(), *ARCH, "-O2", "-std=c++17", "-diag-suppress", "128", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
                "-o", str(lib), str(CSRC / "emu.cu")]
         subprocess.run(cmd, check=True)
     return lib

@@ -34,7 +34,10 @@
 namespace dspx {
 
 constexpr int W8_WARPS = 8;               // warps per CTA, two CTAs per SM (128 registers per thread)
-constexpr int W8_WARPS_WIDE = 20;         // or one 20-warp CTA per SM (<= 102 registers): more warps in flight to
+#ifndef DSPX_W8_WIDE
+#define DSPX_W8_WIDE 20
+#endif
+constexpr int W8_WARPS_WIDE = DSPX_W8_WIDE;         // or one 20-warp CTA per SM (<= 102 registers): more warps in flight to
                                           // cover the shared-memory pipe; +6 % on the feature path, worse for STFT mode
 
 
@@ -179,6 +182,7 @@ template <int R1> struct W8Geo {
 struct W8Tables {            // offsets (in floats) into the packed table blob / shared memory
     int win, tw1, tw2, ptw, ppos, cw, cflag, fdesc, dct, total;
     int rounds, n_slots;     // mel chunks: 32 lanes x rounds (rounds odd)
+    int n_segs;              // run pieces emitted by the mel chunks
     int cw_lanes;            // DCT: coefficient lanes per part (16 or 32)
     int tile_floats;         // per-warp exchange / power tile
     int r1;                  // first-pass radix (4, 8, 16)
@@ -219,9 +223,13 @@ struct W8Power {             // |X|^2 of the bins one pass-3 unit owns, carried 
     float2 lo[9], hi[9];
 };
 
+// The per-warp tile holds, in turn, the FFT exchange data (4 M floats) and then the power spectrum in
+// chunk order followed by the mel segments, the log-mel row and the DCT scratch (all live only after
+// the last FFT pass has been read).
 DSPX_HD int w8_warp_floats(const W8Tables &tb, int n_mels)
 {
-    return (tb.tile_floats + 4 * tb.n_slots + 2 * n_mels + 64 + 3) & ~3;
+    (void)n_mels;
+    return (tb.tile_floats + 3) & ~3;
 }
 
 DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, int n_mels, W8Ctx &c)
@@ -237,9 +245,9 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
     c.dct = tables_smem + tb.dct;
     c.xbuf = reinterpret_cast<float4 *>(warp_smem);
     c.pbuf = reinterpret_cast<float2 *>(warp_smem);
-    c.seg_a = reinterpret_cast<float2 *>(warp_smem + tb.tile_floats);
-    c.seg_b = c.seg_a + tb.n_slots;
-    c.lm = c.seg_b + tb.n_slots;
+    c.seg_a = c.pbuf + (W8_CSTRIDE * tb.n_slots + 16);
+    c.seg_b = c.seg_a + tb.n_segs;
+    c.lm = c.seg_b + tb.n_segs;
     c.dsc = c.lm + n_mels;
 }
 
@@ -739,7 +747,6 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     tb.n_slots = 32 * rounds;
     tb.cw_lanes = n_mfcc <= 16 ? 16 : 32;
     const int dct_blocks = (n_mfcc + tb.cw_lanes - 1) / tb.cw_lanes;
-    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16)) + 16;
     auto al4 = [](int x) { return (x + 3) & ~3; };
     int off = 0;
     tb.win = off; off += 2 * R1 * 32 * 2;
@@ -803,6 +810,8 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         cflag[ci] = (first ? 1 : 0) | (last ? 2 : 0) | (seg << 8);
         if (last) { seg_cnt[ch.run]++; seg++; }
     }
+    tb.n_segs = std::max(seg, 1);
+    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16 + 2 * tb.n_segs + n_mels + 32)) + 16;
     int32_t *ppos = reinterpret_cast<int32_t *>(blob.data() + tb.ppos);
     for (int w = 0; w < units; w++)
         for (int m = 0; m < 9; m++)
