@@ -192,7 +192,7 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     const int units = r1 >= 8 ? r1 / 8 : 1;
     std::vector<W8Power> pw(32 * 2);
     for (uint32_t item = 0; item < p.n_items; item++) {
-        w8_set_item(p, c, item / p.pairs_per_clip, item % p.pairs_per_clip);
+        w8_set_item(p, c, item);
         for (int lane = 0; lane < 32; lane++) {
             const bool share = 2 * cfg->hop_length == e.P && r1 != 16;
             if (r1 == 4 && share) { if (pre) w8_pass1<4, true, true>(c, lane); else w8_pass1<4, false, true>(c, lane); }

@@ -539,7 +539,6 @@ DSPX_HD void w8_store_power(const W8Ctx &c, int lane, int w, const W8Power &pw)
 DSPX_HD void w8_mel_chunks(const W8Ctx &c, int lane)
 {
     float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
-#pragma unroll 3
     for (int r = 0; r < c.rounds; r++) {
         const int ch = lane * c.rounds + r;
         const int flag = c.cflag[ch];                                   // bit0 first, bit1 last, >>8 segment
@@ -599,7 +598,6 @@ DSPX_HD void w8_dct_partial(const W8Ctx &c, int lane, int c0)
     const int q = lane & (cwl - 1), part = lane / cwl;
     const float *col = c.dct + (size_t)(c0 / cwl) * c.n_mels * cwl + q;     // block-major table
     float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 4
     for (int f = part; f < c.n_mels; f += parts) acc = fma2(c.lm[f], bc2(col[f * cwl]), acc);
     c.dsc[lane] = acc;
 }
@@ -617,8 +615,9 @@ DSPX_HD void w8_dct_store(const W8Ctx &c, int lane, int c0)
 }
 
 // set the per-item fields of the context (item = clip * pairs_per_clip + pair)
-DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t clip, uint32_t pair)
+DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
 {
+    const uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
     const int64_t tA = 2 * (int64_t)pair, tB = tA + 1;
     c.validB = tB < p.n_frames;
     const float *base = p.clips + (int64_t)clip * p.clip_stride;
@@ -640,8 +639,10 @@ DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t clip, uint32_t pa
 // the whole per-item sequence; SYNC is __syncwarp() on the device and a no-op in the lane-loop replay
 #if defined(__CUDACC__)
 // pull the next item's samples towards L2 while this one is being transformed
-__device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t clip, uint32_t pair, int lane, int n_fft)
+__device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, int lane, int n_fft)
 {
+    if (item >= p.n_items) return;
+    const uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
     const char *base = reinterpret_cast<const char *>(p.clips + (int64_t)clip * p.clip_stride + 2 * (int64_t)pair * p.hop);
     const int span = (p.hop + n_fft) * 4;                      // bytes covered by the frame pair
     for (int off = lane * 128; off < span; off += 32 * 128)
@@ -672,18 +673,11 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     c.n_mfcc = p.n_mfcc;
     c.rounds = p.tb.rounds;
     c.cw_lanes = p.tb.cw_lanes;
-    // items (clip, pair) advance by n_warps: carried as two counters, no division in the loop
     const uint32_t n_warps = gridDim.x * NW;
-    const uint32_t step_clip = n_warps / p.pairs_per_clip, step_pair = n_warps - step_clip * p.pairs_per_clip;
-    uint32_t item = blockIdx.x * NW + warp;
-    uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
-    for (; item < p.n_items; item += n_warps) {
-        w8_set_item(p, c, clip, pair);
-        clip += step_clip;
-        pair += step_pair;
-        if (pair >= p.pairs_per_clip) { pair -= p.pairs_per_clip; clip++; }
+    for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
+        w8_set_item(p, c, item);
         w8_pass1<R1, PRE, SHARE>(c, lane);
-        if (p.prefetch && item + n_warps < p.n_items) w8_prefetch(p, clip, pair, lane, G::P);
+        if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
         w8_pass2<R1>(c, lane);
         __syncwarp();
