@@ -448,6 +448,17 @@ DSPX_HD void w8_pass3(const W8Ctx &c, int lane, int w, W8Power &pw)
     if (l0) w8_split(r2[3], i2[3], r2[4], i2[4], ptw[8 * 32], pw.lo[8], pw.hi[8]);
 }
 
+// the spectrum is written once and never read back by this kernel: streaming (evict-first) stores keep
+// L2 for the input rows that neighbouring frame pairs share (+2 % measured)
+DSPX_HD void w8_stream_store(float2 *dst, float2 v)
+{
+#if defined(__CUDA_ARCH__)
+    __stcs(dst, v);
+#else
+    *dst = v;
+#endif
+}
+
 // ---- phase C': STFT mode -- same transforms and pairing, but the complex bins go straight to HBM ----
 // X[k] = E + T, X[M-k] = conj(E - T); consecutive lanes hold consecutive bins: coalesced 8-byte stores.
 DSPX_HD void w8_split_store(float2 ar, float2 ai, float2 br, float2 bi, float2 w, float2 *rowA, float2 *rowB,
@@ -460,11 +471,11 @@ DSPX_HD void w8_split_store(float2 ar, float2 ai, float2 br, float2 bi, float2 w
     const float2 ti = fma2(orr, wi, mul2(oi, wr));
     const float2 xr = add2(er, tr), xi = add2(ei, ti);
     const float2 yr = sub2(er, tr), yi = sub2(ti, ei);
-    rowA[k] = make_float2(xr.x, xi.x);
-    rowA[mk] = make_float2(yr.x, yi.x);
+    w8_stream_store(rowA + k, make_float2(xr.x, xi.x));
+    w8_stream_store(rowA + mk, make_float2(yr.x, yi.x));
     if (validB) {
-        rowB[k] = make_float2(xr.y, xi.y);
-        rowB[mk] = make_float2(yr.y, yi.y);
+        w8_stream_store(rowB + k, make_float2(xr.y, xi.y));
+        w8_stream_store(rowB + mk, make_float2(yr.y, yi.y));
     }
 }
 
