@@ -411,3 +411,38 @@ def test_stft_full_size_properties(torch_cuda, fl, hop):
     # the generic kernel agrees with the fast one
     g = stft_batch(x[:2], fl, hop, kernel="generic")
     assert rel_err(g.cpu().numpy(), sx[:2].cpu().numpy()) < 1e-6
+
+
+def test_config2_full_size_properties(torch_cuda):
+    """BASELINE.json configs[1] at full size: 2000 clips x 5 s, MFCC + log-mel + embeddings in one pass.
+    Oracle parity on a sample copied back from the device, plus size-independent properties."""
+    torch = torch_cuda
+    from dsp_final_b200 import synth
+    from dsp_final_b200.batch import embed_stats, features_batch
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+    from oracle import oracle as O
+
+    cfg = MfccConfig(sample_rate=44100, frame_length=1024, hop_length=512)
+    clips = synth.device_clips(2000, seed=1234, device=torch.device("cuda"))
+    out = features_batch(clips, cfg, ("log_mel", "mfcc", "embed"))
+    mf, lm, em = out["mfcc"], out["log_mel"], out["embed"]
+    assert mf.shape == (2000, 429, 13) and lm.shape == (2000, 429, 40) and em.shape == (2000, 26)
+    assert bool(torch.isfinite(mf).all()) and bool(torch.isfinite(lm).all())
+    sel = [0, 399, 1000, 1999]
+    ref = O.features_batch(clips[sel].cpu().numpy(), O.OracleConfig(44100, 1024, 512))
+    for j, i in enumerate(sel):
+        _close(mf[i].cpu().numpy(), ref["mfcc"][j], f"clip {i} mfcc")
+        _close(lm[i].cpu().numpy(), ref["log_mel"][j], f"clip {i} log-mel")
+        _close(em[i].cpu().numpy(), ref["embed"][j], f"clip {i} embed")
+    # permutation equivariance (clips are independent units): bit-identical rows
+    perm = torch.randperm(2000, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    mfp = features_batch(clips[perm].contiguous(), cfg, ("mfcc",))["mfcc"]
+    assert torch.equal(mfp, mf[perm])
+    # two half batches == one batch (what clip sharding across GPUs relies on)
+    a = features_batch(clips[:1000], cfg, ("mfcc",))["mfcc"]
+    b = features_batch(clips[1000:], cfg, ("mfcc",))["mfcc"]
+    assert torch.equal(torch.cat([a, b]), mf)
+    # embeddings are exactly the statistics of the MFCCs that were written
+    assert torch.equal(embed_stats(mf), em)
+    # log-mel never drops below the floor
+    assert float(lm.min()) >= float(np.log(1e-10)) - 1e-4
