@@ -13,6 +13,7 @@
 #include "feat_warp8.cuh"
 #include "fft_generic.cuh"
 #include "retrieval.cuh"
+#include "retrieval_f32.cuh"
 #include "ingest.cuh"
 
 // the ctypes binding (dsp_final_b200/_lib.py) mirrors these layouts; tests assert the same numbers
@@ -716,6 +717,8 @@ size_t dspx_cosine_topk_workspace(int64_t nq, int64_t ndb, int dim, int k)
     if (nq < 0 || ndb < 0 || dim <= 0 || k <= 0) return 0;
     size_t b = align256((size_t)nq * dim * 8) + align256((size_t)ndb * dim * 8);
     b += align256((size_t)nq * TK_MAX_SPLITS * k * 8) + align256((size_t)nq * TK_MAX_SPLITS * k * 4);
+    b += align256((size_t)((nq + TKF_QPC - 1) / TKF_QPC) * TKF_QPC * dim * 4);    // tile-transposed float copies
+    b += align256((size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * dim * 4);
     return b + 1024;
 }
 
@@ -742,8 +745,26 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     double *pscore = reinterpret_cast<double *>(ws);
     ws += align256((size_t)nq * TK_MAX_SPLITS * k * 8);
     int32_t *pidx = reinterpret_cast<int32_t *>(ws);
+    ws += align256((size_t)nq * TK_MAX_SPLITS * k * 4);
+    float *qf_t = reinterpret_cast<float *>(ws);
+    const size_t qf_bytes = (size_t)((nq + TKF_QPC - 1) / TKF_QPC) * TKF_QPC * dim * 4;
+    ws += align256(qf_bytes);
+    float *dbf_t = reinterpret_cast<float *>(ws);
+    const size_t dbf_bytes = (size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * dim * 4;
+    // FP32 pre-filter + exact float64 re-score: single-chunk dimensions and lists that fit beside the tiles
+    const bool prefilter = !getenv("DSPX_TOPK_F64") && dim <= 32 && topk_f32_smem_bytes(dim, k, dim == 26 ? 26 : 32) <= 200 * 1024;
 
-    if (dtype == DSPX_DTYPE_F32) {
+    if (prefilter) {
+        DSPX_CUDA_CHECK(cudaMemsetAsync(qf_t, 0, qf_bytes, st));              // zero padding of the last tiles
+        DSPX_CUDA_CHECK(cudaMemsetAsync(dbf_t, 0, dbf_bytes, st));
+        if (dtype == DSPX_DTYPE_F32) {
+            normalize_rows_tiled_kernel<float><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((const float *)q_dev, nq, dim, qn, qf_t, TKF_QPC);
+            normalize_rows_tiled_kernel<float><<<(unsigned)((ndb + 127) / 128), 128, 0, st>>>((const float *)db_dev, ndb, dim, dbn, dbf_t, TK_ROWS);
+        } else {
+            normalize_rows_tiled_kernel<double><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((const double *)q_dev, nq, dim, qn, qf_t, TKF_QPC);
+            normalize_rows_tiled_kernel<double><<<(unsigned)((ndb + 127) / 128), 128, 0, st>>>((const double *)db_dev, ndb, dim, dbn, dbf_t, TK_ROWS);
+        }
+    } else if (dtype == DSPX_DTYPE_F32) {
         normalize_rows_kernel<float><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((const float *)q_dev, nq, dim, qn);
         normalize_rows_kernel<float><<<(unsigned)((ndb + 127) / 128), 128, 0, st>>>((const float *)db_dev, ndb, dim, dbn);
     } else {
@@ -767,7 +788,43 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     tp.idx_out = tp.n_splits == 1 ? idx_out_dev : pidx;
     tp.score_out = tp.n_splits == 1 ? score_out_dev : pscore;
     dim3 grid((unsigned)((nq + TK_QPC - 1) / TK_QPC), (unsigned)tp.n_splits);
-    if (dim == 26) {                                   // MFCC embeddings: 2 x 13, the whole vector in one chunk
+    if (prefilter) {
+        TopkF32Params fp{};
+        // 128 queries per CTA here: recompute the database split for that grid
+        const int64_t qtiles = (nq + TKF_QPC - 1) / TKF_QPC;
+        // one CTA per SM: pick the split count whose grid fills whole waves (every extra split also restarts
+        // the running lists, which costs insertions -- the 2 % per split term)
+        int64_t max_sp = (ndb + 8 * TK_ROWS - 1) / (8 * TK_ROWS);
+        if (max_sp > 16) max_sp = 16;
+        if (max_sp < 1) max_sp = 1;
+        int64_t sp = 1;
+        double best = 1e30;
+        for (int64_t c = 1; c <= max_sp; c++) {
+            const double waves = (double)((qtiles * c + sm - 1) / sm);
+            const double cost = waves / (double)c * (1.0 + 0.02 * (double)c);
+            if (cost < best - 1e-12) { best = cost; sp = c; }
+        }
+        int64_t rows = (ndb + sp - 1) / sp;
+        rows = (rows + TK_ROWS - 1) / TK_ROWS * TK_ROWS;
+        tp.rows_per_split = rows;
+        tp.n_splits = (int)((ndb + rows - 1) / rows);
+        tp.idx_out = tp.n_splits == 1 ? idx_out_dev : pidx;
+        tp.score_out = tp.n_splits == 1 ? score_out_dev : pscore;
+        fp.base = tp;
+        fp.qf_t = qf_t;
+        fp.dbf_t = dbf_t;
+        fp.eps = 4e-6f + (float)dim * 1.2e-7f;         // > 2 * 2^-24 * (dim + 2): bound on |s32 - s64| for unit vectors
+        dim3 fgrid((unsigned)qtiles, (unsigned)tp.n_splits);
+        if (dim == 26) {
+            const size_t smem = topk_f32_smem_bytes(dim, k, 26);
+            DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_f32_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cosine_topk_f32_kernel<26><<<fgrid, TKF_WARPS * 32, smem, st>>>(fp);
+        } else {
+            const size_t smem = topk_f32_smem_bytes(dim, k, 32);
+            DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cosine_topk_f32_kernel<32><<<fgrid, TKF_WARPS * 32, smem, st>>>(fp);
+        }
+    } else if (dim == 26) {                            // MFCC embeddings: 2 x 13, the whole vector in one chunk
         const size_t smem = topk_smem_bytes(dim, k, 26);
         DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cosine_topk_kernel<26><<<grid, TK_WARPS * 32, smem, st>>>(tp);

@@ -286,6 +286,27 @@ def test_retrieval_vs_oracle_shapes(torch_cuda, nq, ndb, dim, k):
     assert R.hits_at_k(idx, k, t_db, t_q) == O.hits_at_k(want_idx, k, t_db, t_q)
 
 
+@pytest.mark.parametrize("dim,k", [(26, 20), (16, 7), (32, 40)])
+def test_retrieval_float32_collisions(torch_cuda, dim, k):
+    """The ranking kernel filters in float32 and re-scores in float64: clusters of database rows whose scores
+    differ only below float32 resolution (and exact duplicates) must still come back in the oracle's order."""
+    from dsp_final_b200 import retrieval as R
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(dim * 31 + k)
+    nq, ndb = 150, 6000
+    q = rng.standard_normal((nq, dim))
+    db = rng.standard_normal((ndb, dim))
+    for c in range(12):                                    # 12 clusters of 60 rows around a query direction
+        rows = rng.choice(ndb, 60, replace=False)
+        db[rows] = q[c] * rng.uniform(0.5, 2.0, (60, 1)) + 1e-9 * rng.standard_normal((60, dim))
+        db[rows[:5]] = db[rows[5]]                         # plus exact duplicates
+    idx, sc = R.cosine_topk(q, db, k, return_scores=True)
+    want_idx, want_sc = O.cosine_topk(q, db, k, return_scores=True)
+    assert np.array_equal(idx, want_idx)
+    assert np.array_equal(sc, want_sc)
+
+
 def test_retrieval_sweep_config3(torch_cuda):
     """BASELINE.json configs[2] in miniature: frame x hop sweep, fold-5 queries vs folds 1-4,
     identical index lists and identical Top-10 / Top-20 against the oracle on the same embeddings."""
