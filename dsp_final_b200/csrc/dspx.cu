@@ -3,6 +3,7 @@
 // kernels included below; this file only validates arguments and launches.
 #include <cstdarg>
 #include <cstddef>
+#include <cstring>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -14,6 +15,7 @@
 #include "fft_generic.cuh"
 #include "retrieval.cuh"
 #include "retrieval_f32.cuh"
+#include "retrieval_tc.cuh"
 #include "ingest.cuh"
 
 // the ctypes binding (dsp_final_b200/_lib.py) mirrors these layouts; tests assert the same numbers
@@ -717,8 +719,9 @@ size_t dspx_cosine_topk_workspace(int64_t nq, int64_t ndb, int dim, int k)
     if (nq < 0 || ndb < 0 || dim <= 0 || k <= 0) return 0;
     size_t b = align256((size_t)nq * dim * 8) + align256((size_t)ndb * dim * 8);
     b += align256((size_t)nq * TK_MAX_SPLITS * k * 8) + align256((size_t)nq * TK_MAX_SPLITS * k * 4);
-    b += align256((size_t)((nq + TKF_QPC - 1) / TKF_QPC) * TKF_QPC * dim * 4);    // tile-transposed float copies
-    b += align256((size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * dim * 4);
+    // float copies for the filter kernels: 32 floats per row covers both layouts (dim <= 32 there)
+    b += align256((size_t)((nq + TC_QT - 1) / TC_QT) * TC_QT * TC_KPAD * 4);
+    b += align256((size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4);
     return b + 1024;
 }
 
@@ -747,13 +750,30 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     int32_t *pidx = reinterpret_cast<int32_t *>(ws);
     ws += align256((size_t)nq * TK_MAX_SPLITS * k * 4);
     float *qf_t = reinterpret_cast<float *>(ws);
-    const size_t qf_bytes = (size_t)((nq + TKF_QPC - 1) / TKF_QPC) * TKF_QPC * dim * 4;
+    const size_t qf_bytes = (size_t)((nq + TC_QT - 1) / TC_QT) * TC_QT * TC_KPAD * 4;
     ws += align256(qf_bytes);
     float *dbf_t = reinterpret_cast<float *>(ws);
-    const size_t dbf_bytes = (size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * dim * 4;
-    // FP32 pre-filter + exact float64 re-score: single-chunk dimensions and lists that fit beside the tiles
-    const bool prefilter = !getenv("DSPX_TOPK_F64") && dim <= 32 && topk_f32_smem_bytes(dim, k, dim == 26 ? 26 : 32) <= 200 * 1024;
+    const size_t dbf_bytes = (size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4;
+    // Filter kernels (single-chunk dimensions, lists that fit beside the tiles), all with exact float64 re-scoring:
+    // tensor-core TF32 filter, else packed-FP32 filter, else the all-float64 kernel.  DSPX_TOPK = tc | f32 | f64 forces one.
+    const char *force = getenv("DSPX_TOPK");
+    const bool want_f64 = getenv("DSPX_TOPK_F64") || (force && !strcmp(force, "f64"));
+    const bool tc_ok = dim <= 32 && k <= TC_MAX_K;
+    const bool f32_ok = dim <= 32 && topk_f32_smem_bytes(dim, k, dim == 26 ? 26 : 32) <= 200 * 1024;
+    const bool use_tc = !want_f64 && tc_ok && !(force && !strcmp(force, "f32") && f32_ok);
+    const bool prefilter = !want_f64 && !use_tc && f32_ok;
 
+    if (use_tc) {
+        DSPX_CUDA_CHECK(cudaMemsetAsync(qf_t, 0, qf_bytes, st));              // zero padding: columns >= dim, rows >= n
+        DSPX_CUDA_CHECK(cudaMemsetAsync(dbf_t, 0, dbf_bytes, st));
+        if (dtype == DSPX_DTYPE_F32) {
+            normalize_rows_pad32_kernel<float><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((const float *)q_dev, nq, dim, qn, qf_t);
+            normalize_rows_pad32_kernel<float><<<(unsigned)((ndb + 127) / 128), 128, 0, st>>>((const float *)db_dev, ndb, dim, dbn, dbf_t);
+        } else {
+            normalize_rows_pad32_kernel<double><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((const double *)q_dev, nq, dim, qn, qf_t);
+            normalize_rows_pad32_kernel<double><<<(unsigned)((ndb + 127) / 128), 128, 0, st>>>((const double *)db_dev, ndb, dim, dbn, dbf_t);
+        }
+    } else
     if (prefilter) {
         DSPX_CUDA_CHECK(cudaMemsetAsync(qf_t, 0, qf_bytes, st));              // zero padding of the last tiles
         DSPX_CUDA_CHECK(cudaMemsetAsync(dbf_t, 0, dbf_bytes, st));
@@ -788,12 +808,10 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     tp.idx_out = tp.n_splits == 1 ? idx_out_dev : pidx;
     tp.score_out = tp.n_splits == 1 ? score_out_dev : pscore;
     dim3 grid((unsigned)((nq + TK_QPC - 1) / TK_QPC), (unsigned)tp.n_splits);
-    if (prefilter) {
-        TopkF32Params fp{};
-        // 128 queries per CTA here: recompute the database split for that grid
-        const int64_t qtiles = (nq + TKF_QPC - 1) / TKF_QPC;
+    if (use_tc || prefilter) {
         // one CTA per SM: pick the split count whose grid fills whole waves (every extra split also restarts
-        // the running lists, which costs insertions -- the 2 % per split term)
+        // the running lists, which costs insertions -- the per-split penalty)
+        const int64_t qtiles = use_tc ? (nq + TC_QT - 1) / TC_QT : (nq + TKF_QPC - 1) / TKF_QPC;
         int64_t max_sp = (ndb + 8 * TK_ROWS - 1) / (8 * TK_ROWS);
         if (max_sp > 16) max_sp = 16;
         if (max_sp < 1) max_sp = 1;
@@ -810,6 +828,22 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
         tp.n_splits = (int)((ndb + rows - 1) / rows);
         tp.idx_out = tp.n_splits == 1 ? idx_out_dev : pidx;
         tp.score_out = tp.n_splits == 1 ? score_out_dev : pscore;
+        if (use_tc) {
+            TopkTcParams cp{};
+            cp.base = tp;
+            cp.qf = qf_t;
+            cp.dbf = dbf_t;
+            dim3 cgrid((unsigned)qtiles, (unsigned)tp.n_splits);
+            const size_t smem = topk_tc_smem_bytes(k);
+            if (dim == 26) {
+                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_tc_smem_bytes(TC_MAX_K)));
+                cosine_topk_tc_kernel<26><<<cgrid, TC_THREADS, smem, st>>>(cp);
+            } else {
+                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_tc_smem_bytes(TC_MAX_K)));
+                cosine_topk_tc_kernel<0><<<cgrid, TC_THREADS, smem, st>>>(cp);
+            }
+        } else {
+        TopkF32Params fp{};
         fp.base = tp;
         fp.qf_t = qf_t;
         fp.dbf_t = dbf_t;
@@ -823,6 +857,7 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
             const size_t smem = topk_f32_smem_bytes(dim, k, 32);
             DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             cosine_topk_f32_kernel<32><<<fgrid, TKF_WARPS * 32, smem, st>>>(fp);
+        }
         }
     } else if (dim == 26) {                            // MFCC embeddings: 2 x 13, the whole vector in one chunk
         const size_t smem = topk_smem_bytes(dim, k, 26);

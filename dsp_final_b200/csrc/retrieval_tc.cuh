@@ -1,0 +1,322 @@
+// retrieval_tc.cuh -- exact cosine top-k with a tensor-core (tcgen05, TF32) pre-filter.
+//
+// Same contract as cosine_topk_kernel (retrieval.cuh): float64 scores accumulated left to right with fused
+// multiply-adds, descending order, ties to the lower database index -- the result is bit-identical.  The
+// similarity matrix q . db^T is a GEMM, so the scores that only have to be *compared* against each query's
+// current k-th score are produced by the 5th-generation tensor cores; the few pairs that pass are re-scored
+// exactly in float64.  Replaces the argsort over the dense matrix of src/retrieval/retrieval.py:25-49.
+//
+// Arithmetic: kind::tf32 keeps 10 mantissa bits of each operand (~1e-3 on a unit-vector dot product), which
+// would pass far too many pairs for tightly clustered embeddings.  Each float32 value v is therefore split
+// into hi = v with the low 13 mantissa bits cleared (exact in TF32) and lo = v - hi, and the product is
+// accumulated as A_lo B_hi + A_hi B_lo + A_hi B_hi: three K = 32 passes into the same float32 accumulator.
+// What is dropped (A_lo B_lo and the truncation of lo) is below 3 * 2^-20 of sum |q_i d_i| <= 1; measured
+// against float64 on unit vectors (benchmarks/micro/umma_tf32.cu) the error is 5e-7.  TC_EPS = 2e-5 leaves
+// a factor 40, so every pair with s64 >= thr64 has s_tc > thr32 = float(thr64 - eps) and is re-scored.
+//
+// Structure of a CTA (352 threads, one per SM), 256 queries x one database split:
+//   warps 0-7  epilogue: thread = one query.  tcgen05.ld its accumulator row (32 columns at a time), compare
+//              with the thread's threshold, release the TMEM buffer, then re-score the candidates in float64
+//              and insert them into the thread's own sorted list in shared memory (rows arrive in index
+//              order, so "strictly better than the current worst" keeps ties at the lower index).
+//   warps 8-9  producers: database tile (128 rows x 32 floats, zero padded) from global memory, split into
+//              hi / lo, stored K-major under the 128-byte swizzle the tensor core expects; mbarrier hand-off.
+//   warp 10    one lane issues 2 x 12 tcgen05.mma (M 128, N 128, K 8) per tile into a double-buffered
+//              512-column TMEM accumulator and commits to the mbarriers of the smem stage and the buffer.
+#pragma once
+
+#include "retrieval.cuh"
+
+namespace dspx {
+
+#if defined(__CUDACC__)
+
+constexpr int TC_QT = 256;            // queries per CTA: two 128-row A tiles
+constexpr int TC_ROWS = 128;          // database rows per tile (UMMA N)
+constexpr int TC_STAGES = 2;
+constexpr int TC_EPI_THREADS = 256, TC_PROD_THREADS = 64;
+constexpr int TC_THREADS = TC_EPI_THREADS + TC_PROD_THREADS + 32;
+constexpr int TC_KPAD = 32;           // floats per row of the padded float copies (one 128-byte swizzle row)
+constexpr double TC_EPS = 2e-5;
+constexpr int TC_MAX_K = 28;          // the per-thread lists ([k][256] doubles + ints) share smem with the tiles
+
+template <typename T>
+__global__ void normalize_rows_pad32_kernel(const T *x, int64_t n, int dim, double *out64, float *out32)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const T *row = x + (size_t)r * dim;
+    double s = 0.0;
+    for (int c = 0; c < dim; c++) {
+        const double v = (double)row[c];
+        s = fma(v, v, s);
+    }
+    const double inv = sqrt(s) + 1e-10;
+    float *t = out32 + (size_t)r * TC_KPAD;
+    for (int c = 0; c < dim; c++) {
+        const double v = (double)row[c] / inv;
+        out64[(size_t)r * dim + c] = v;
+        t[c] = (float)v;
+    }
+}
+
+struct TopkTcParams {
+    TopkParams base;
+    const float *qf;        // [ceil(nq / 256) * 256][32], zero padded
+    const float *dbf;       // [ceil(ndb / 128) * 128][32], zero padded
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol error traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    for (uint32_t spin = 0;; spin++) {
+        uint32_t ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 28)) __trap();
+    }
+}
+
+// K-major operand tile under SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t tc_desc(const void *tile)
+{
+    return (uint64_t)((tc_smem_u32(tile) >> 4) & 0x3fff) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+
+// split a float4 into TF32-exact high parts and residuals; store both at the swizzled chunk position
+__device__ __forceinline__ void tc_store_split(unsigned char *hi_tile, unsigned char *lo_tile, int row, int chunk, float4 v)
+{
+    const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    *reinterpret_cast<float4 *>(hi_tile + off) = h;
+    *reinterpret_cast<float4 *>(lo_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+// 32 accumulator columns of this thread's TMEM lane -> bit j set when column j passes the threshold
+__device__ __forceinline__ uint32_t tc_ld_mask(uint32_t taddr, float thr32)
+{
+    uint32_t v[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) m |= (__uint_as_float(v[j]) > thr32) ? (1u << j) : 0u;
+    return m;
+}
+
+inline size_t topk_tc_smem_bytes(int k)
+{
+    return 1024 + (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * k * 12 + 128;
+}
+
+// DIM > 0: the embedding dimension is a compile-time constant (all loads of the exact dot product in flight at
+// once); DIM == 0: any dim <= 32.
+template <int DIM>
+__global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const TopkTcParams pp)
+{
+    const TopkParams &p = pp.base;
+    extern __shared__ unsigned char tc_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *a_hi = base;                                   // [2][128 rows x 128 B]
+    unsigned char *a_lo = a_hi + 2 * TC_ROWS * 128;
+    unsigned char *b_hi = a_lo + 2 * TC_ROWS * 128;               // [TC_STAGES][128 x 128 B]
+    unsigned char *b_lo = b_hi + TC_STAGES * TC_ROWS * 128;
+    double *s_ls = reinterpret_cast<double *>(b_lo + TC_STAGES * TC_ROWS * 128);     // [k][256]
+    int32_t *s_li = reinterpret_cast<int32_t *>(s_ls + (size_t)p.k * TC_QT);         // [k][256]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_li + (size_t)p.k * TC_QT);       // 8-byte aligned: k * 256 * 4
+    uint64_t *full_b = bars, *empty_b = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dim = DIM > 0 ? DIM : p.dim;
+    const int64_t q0 = (int64_t)blockIdx.x * TC_QT;
+    const int split = blockIdx.y;
+    const int64_t r_begin = (int64_t)split * p.rows_per_split;    // multiple of TC_ROWS
+    int64_t r_end = r_begin + p.rows_per_split;
+    if (r_end > p.ndb) r_end = p.ndb;
+    const int64_t n_tiles = (r_end - r_begin + TC_ROWS - 1) / TC_ROWS;
+
+    // ---- set-up: query tiles (split, swizzled), barriers, TMEM ----------------------------------
+    for (int c = tid; c < TC_QT * 8; c += TC_THREADS) {
+        const int row = c >> 3, chunk = c & 7, a = row >> 7;
+        const float4 v = *reinterpret_cast<const float4 *>(pp.qf + ((size_t)(q0 + row) * TC_KPAD + chunk * 4));
+        tc_store_split(a_hi + a * TC_ROWS * 128, a_lo + a * TC_ROWS * 128, row & 127, chunk, v);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { tc_mbar_init(&full_b[s], TC_PROD_THREADS); tc_mbar_init(&empty_b[s], 1); }
+        for (int b = 0; b < 2; b++) { tc_mbar_init(&acc_full[b], 1); tc_mbar_init(&acc_empty[b], TC_EPI_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == TC_THREADS / 32 - 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;");               // the A tiles were written through the generic proxy
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot;
+
+    if (tid < TC_EPI_THREADS) {
+        // ===== epilogue: one query per thread =====
+        const int ql = tid;                                        // = (warp >> 2) * 128 + (warp & 3) * 32 + lane
+        const int64_t gq = q0 + ql;
+        const bool active = gq < p.nq;
+        const double *qrow = p.qn + (size_t)(active ? gq : 0) * dim;
+        double *ls = s_ls + ql;                                    // element e at ls[e * TC_QT]
+        int32_t *li = s_li + ql;
+        const int k = p.k;
+        int cnt = 0;
+        double thr = 0.0;
+        float thr32 = active ? -INFINITY : INFINITY;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TC_ROWS);
+        for (int64_t t = 0; t < n_tiles; t++) {
+            const int buf = (int)(t & 1);
+            tc_mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+            __syncwarp();                                          // tcgen05.ld is warp-collective
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            uint32_t m[4];
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) m[cb] = tc_ld_mask(lane_base + (uint32_t)(buf * 2 * TC_ROWS + cb * 32), thr32);
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);        // the tensor core may overwrite this buffer now
+            const int64_t tile = r_begin + t * TC_ROWS;
+            // candidates of all lanes are processed in lock step, each lane in increasing row order
+            while (__any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0)) {
+                int64_t row = -1;
+#pragma unroll
+                for (int cb = 0; cb < 4; cb++) {
+                    if (row < 0 && m[cb]) {
+                        const int j = __ffs(m[cb]) - 1;
+                        m[cb] &= m[cb] - 1;
+                        row = tile + cb * 32 + j;
+                    }
+                }
+                if (row < 0 || row >= r_end) continue;
+                const double *d = p.dbn + (size_t)row * dim;
+                double s = 0.0;
+                if (DIM > 0) {
+                    double dv[DIM > 0 ? DIM : 1], qv[DIM > 0 ? DIM : 1];
+#pragma unroll
+                    for (int c = 0; c < DIM; c++) { dv[c] = d[c]; qv[c] = qrow[c]; }
+#pragma unroll
+                    for (int c = 0; c < DIM; c++) s = fma(qv[c], dv[c], s);
+                } else {
+                    int c = 0;
+                    for (; c + 8 <= dim; c += 8) {
+                        double dv[8], qv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { dv[j] = d[c + j]; qv[j] = qrow[c + j]; }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) s = fma(qv[j], dv[j], s);
+                    }
+                    for (; c < dim; c++) s = fma(qrow[c], d[c], s);
+                }
+                if (cnt == k && !(s > thr)) continue;              // ties with the current worst keep the lower index
+                int pos = cnt < k ? cnt : k - 1;
+                while (pos > 0 && ls[(size_t)(pos - 1) * TC_QT] < s) {
+                    ls[(size_t)pos * TC_QT] = ls[(size_t)(pos - 1) * TC_QT];
+                    li[(size_t)pos * TC_QT] = li[(size_t)(pos - 1) * TC_QT];
+                    pos--;
+                }
+                ls[(size_t)pos * TC_QT] = s;
+                li[(size_t)pos * TC_QT] = (int32_t)row;
+                if (cnt < k) cnt++;
+                if (cnt == k) {
+                    thr = ls[(size_t)(k - 1) * TC_QT];
+                    thr32 = __double2float_rd(thr - TC_EPS);
+                }
+            }
+        }
+        if (active) {
+            const size_t o = ((size_t)gq * p.n_splits + split) * k;
+            for (int e = 0; e < k; e++) {
+                const bool have = e < cnt;
+                p.idx_out[o + e] = have ? li[(size_t)e * TC_QT] : -1;
+                if (p.score_out) p.score_out[o + e] = have ? ls[(size_t)e * TC_QT] : -INFINITY;
+            }
+        }
+    } else if (tid < TC_EPI_THREADS + TC_PROD_THREADS) {
+        // ===== producers: database tile -> hi / lo operand tiles =====
+        const int ptid = tid - TC_EPI_THREADS;
+        for (int64_t t = 0; t < n_tiles; t++) {
+            const int s = (int)(t % TC_STAGES);
+            tc_mbar_wait(&empty_b[s], (uint32_t)(((t / TC_STAGES) & 1) ^ 1));
+            const float *src = pp.dbf + (size_t)(r_begin + t * TC_ROWS) * TC_KPAD;
+            unsigned char *hi = b_hi + s * TC_ROWS * 128, *lo = b_lo + s * TC_ROWS * 128;
+#pragma unroll 4
+            for (int c = ptid; c < TC_ROWS * 8; c += TC_PROD_THREADS) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + c);
+                tc_store_split(hi, lo, c >> 3, c & 7, v);
+            }
+            asm volatile("fence.proxy.async.shared::cta;");
+            tc_mbar_arrive(&full_b[s]);
+        }
+    } else if (lane == 0) {
+        // ===== tensor-core issue: one thread =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int64_t t = 0; t < n_tiles; t++) {
+            const int s = (int)(t % TC_STAGES), buf = (int)(t & 1);
+            tc_mbar_wait(&acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
+            tc_mbar_wait(&full_b[s], (uint32_t)((t / TC_STAGES) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint64_t bh = tc_desc(b_hi + s * TC_ROWS * 128), bl = tc_desc(b_lo + s * TC_ROWS * 128);
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const uint64_t ah = tc_desc(a_hi + a * TC_ROWS * 128), al = tc_desc(a_lo + a * TC_ROWS * 128);
+                const uint32_t d = tmem + (uint32_t)(buf * 2 * TC_ROWS + a * TC_ROWS);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, al + 2 * kk, bh + 2 * kk, idesc, kk > 0);     // small terms first
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+            }
+            tc_commit(&empty_b[s]);                                // smem stage free once these MMAs have read it
+            tc_commit(&acc_full[buf]);                             // accumulators complete
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    __syncwarp();
+    if (warp == TC_THREADS / 32 - 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+#endif
+
+}  // namespace dspx
