@@ -722,6 +722,7 @@ size_t dspx_cosine_topk_workspace(int64_t nq, int64_t ndb, int dim, int k)
     // float copies for the filter kernels: 32 floats per row covers both layouts (dim <= 32 there)
     b += align256((size_t)((nq + TC_QT - 1) / TC_QT) * TC_QT * TC_KPAD * 4);
     b += align256((size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4);
+    b += align256((size_t)nq * 8);                                                // thresholds shared between splits
     return b + 1024;
 }
 
@@ -754,6 +755,8 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     ws += align256(qf_bytes);
     float *dbf_t = reinterpret_cast<float *>(ws);
     const size_t dbf_bytes = (size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4;
+    ws += align256(dbf_bytes);
+    unsigned long long *shared_thr = reinterpret_cast<unsigned long long *>(ws);
     // Filter kernels (single-chunk dimensions, lists that fit beside the tiles), all with exact float64 re-scoring:
     // tensor-core TF32 filter, else packed-FP32 filter, else the all-float64 kernel.  DSPX_TOPK = tc | f32 | f64 forces one.
     const char *force = getenv("DSPX_TOPK");
@@ -822,6 +825,10 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
             const double cost = waves / (double)c * (1.0 + 0.02 * (double)c);
             if (cost < best - 1e-12) { best = cost; sp = c; }
         }
+        if (const char *e = getenv("DSPX_TOPK_SPLITS")) {                       // tuning knob
+            const int64_t v = atoll(e);
+            if (v >= 1 && v <= TK_MAX_SPLITS) sp = v;
+        }
         int64_t rows = (ndb + sp - 1) / sp;
         rows = (rows + TK_ROWS - 1) / TK_ROWS * TK_ROWS;
         tp.rows_per_split = rows;
@@ -833,6 +840,8 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
             cp.base = tp;
             cp.qf = qf_t;
             cp.dbf = dbf_t;
+            cp.shared_thr = tp.n_splits > 1 ? shared_thr : nullptr;
+            if (cp.shared_thr) DSPX_CUDA_CHECK(cudaMemsetAsync(shared_thr, 0, (size_t)nq * 8, st));
             dim3 cgrid((unsigned)qtiles, (unsigned)tp.n_splits);
             const size_t smem = topk_tc_smem_bytes(k);
             if (dim == 26) {
@@ -875,6 +884,13 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     }
     return DSPX_OK;
 }
+
+#ifdef DSPX_TC_PROFILE
+extern "C" int dspx_debug_tc_prof(long long *out16)
+{
+    return cudaMemcpyFromSymbol(out16, dspx::tc_prof, 16 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int dspx_cosine_matrix(const void *q_dev, int64_t nq, const void *db_dev, int64_t ndb, int dim, int dtype,
                        double *sims_out_dev, void *workspace_dev, size_t workspace_bytes, void *stream)

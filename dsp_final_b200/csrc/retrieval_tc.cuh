@@ -38,6 +38,7 @@ constexpr int TC_EPI_THREADS = 256, TC_PROD_THREADS = 64;
 constexpr int TC_THREADS = TC_EPI_THREADS + TC_PROD_THREADS + 32;
 constexpr int TC_KPAD = 32;           // floats per row of the padded float copies (one 128-byte swizzle row)
 constexpr double TC_EPS = 2e-5;
+constexpr int TC_FIFO = 8, TC_FIFO_TRIGGER = 4;   // pending candidates per query: ring size / drain trigger
 constexpr int TC_MAX_K = 28;          // the per-thread lists ([k][256] doubles + ints) share smem with the tiles
 
 template <typename T>
@@ -60,11 +61,34 @@ __global__ void normalize_rows_pad32_kernel(const T *x, int64_t n, int dim, doub
     }
 }
 
+#ifdef DSPX_TC_PROFILE
+// per-role cycle counters of CTA (0, 0): [0] mma wait acc_empty [1] mma wait full_b [2] mma issue [3] producer wait
+// [4] producer store [5] epilogue wait acc_full [6] epilogue masks [7] epilogue enqueue+drain [8] tiles [9] total
+__device__ long long tc_prof[16];
+#define TC_PROF_T0() long long _pt = clock64()
+#define TC_PROF_ADD(i) do { const long long _n = clock64(); if (blockIdx.x == 0 && blockIdx.y == 0) tc_prof_local[i] += _n - _pt; _pt = _n; } while (0)
+#else
+#define TC_PROF_T0()
+#define TC_PROF_ADD(i)
+#endif
+
 struct TopkTcParams {
     TopkParams base;
     const float *qf;        // [ceil(nq / 256) * 256][32], zero padded
     const float *dbf;       // [ceil(ndb / 128) * 128][32], zero padded
+    unsigned long long *shared_thr;   // [nq] order-encoded k-th scores shared by the splits of a query (null: one split)
 };
+
+// order-preserving double <-> uint64 (0 is below every double): lets atomicMax maintain a shared threshold
+__device__ __forceinline__ unsigned long long tc_enc(double d)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double tc_dec(unsigned long long u)
+{
+    return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
+}
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -137,9 +161,54 @@ __device__ __forceinline__ uint32_t tc_ld_mask(uint32_t taddr, float thr32)
     return m;
 }
 
+// the same for 64 columns: both loads are in flight before the single wait
+__device__ __forceinline__ void tc_ld_mask2(uint32_t taddr, float thr32, uint32_t &m0, uint32_t &m1)
+{
+    uint32_t v[64];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                 "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+                 "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+                   "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+                   "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+                   "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+                   "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    // Almost every block of 32 columns is entirely below the threshold: a max tree (3-input FMNMX, log depth)
+    // decides that in 16 instructions; the bit mask is only built when some lane of the warp has a hit.
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t *w = v + 32 * h;
+        float mx[11];
+#pragma unroll
+        for (int j = 0; j < 10; j++)
+            mx[j] = fmaxf(fmaxf(__uint_as_float(w[3 * j]), __uint_as_float(w[3 * j + 1])), __uint_as_float(w[3 * j + 2]));
+        mx[10] = fmaxf(__uint_as_float(w[30]), __uint_as_float(w[31]));
+        const float t0 = fmaxf(fmaxf(mx[0], mx[1]), mx[2]), t1 = fmaxf(fmaxf(mx[3], mx[4]), mx[5]);
+        const float t2 = fmaxf(fmaxf(mx[6], mx[7]), mx[8]), t3 = fmaxf(mx[9], mx[10]);
+        const float top = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+        if (__any_sync(0xffffffffu, top > thr32)) {
+            uint32_t part[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 32; j++) part[j & 3] |= (__uint_as_float(w[j]) > thr32) ? (1u << j) : 0u;
+            const uint32_t mm = (part[0] | part[1]) | (part[2] | part[3]);
+            if (h == 0) a = mm; else b = mm;
+        }
+    }
+    m0 = a;
+    m1 = b;
+}
+
 inline size_t topk_tc_smem_bytes(int k)
 {
-    return 1024 + (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * k * 12 + 128;
+    return (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 4 + 128;
 }
 
 // DIM > 0: the embedding dimension is a compile-time constant (all loads of the exact dot product in flight at
@@ -148,15 +217,16 @@ template <int DIM>
 __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const TopkTcParams pp)
 {
     const TopkParams &p = pp.base;
-    extern __shared__ unsigned char tc_raw[];
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *a_hi = base;                                   // [2][128 rows x 128 B]
+    extern __shared__ __align__(1024) unsigned char tc_raw[];     // the 128-byte swizzle pattern repeats every 1024 bytes
+    if (tc_smem_u32(tc_raw) & 1023u) __trap();
+    unsigned char *a_hi = tc_raw;                                 // [2][128 rows x 128 B]
     unsigned char *a_lo = a_hi + 2 * TC_ROWS * 128;
     unsigned char *b_hi = a_lo + 2 * TC_ROWS * 128;               // [TC_STAGES][128 x 128 B]
     unsigned char *b_lo = b_hi + TC_STAGES * TC_ROWS * 128;
     double *s_ls = reinterpret_cast<double *>(b_lo + TC_STAGES * TC_ROWS * 128);     // [k][256]
     int32_t *s_li = reinterpret_cast<int32_t *>(s_ls + (size_t)p.k * TC_QT);         // [k][256]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_li + (size_t)p.k * TC_QT);       // 8-byte aligned: k * 256 * 4
+    int32_t *s_fifo = s_li + (size_t)p.k * TC_QT;                                    // [TC_FIFO][256] pending candidate rows
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_fifo + TC_FIFO * TC_QT);         // 8-byte aligned
     uint64_t *full_b = bars, *empty_b = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
@@ -200,33 +270,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         int32_t *li = s_li + ql;
         const int k = p.k;
         int cnt = 0;
-        double thr = 0.0;
-        float thr32 = active ? -INFINITY : INFINITY;
+        double thr = 0.0;                                          // k-th score of this thread's list once it is full
+        // Splits of one query share the best k-th score any of them has reached (gthr): a row scoring below it
+        // can never enter the merged top-k, so it is neither re-scored nor inserted.  This only prunes work --
+        // every member of the final top-k scores >= gthr at all times and is among the k best of its own split.
+        unsigned long long *gslot = (pp.shared_thr && active) ? pp.shared_thr + gq : nullptr;
+        double gthr = -INFINITY;
+        unsigned long long genc = 0;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TC_ROWS);
-        for (int64_t t = 0; t < n_tiles; t++) {
-            const int buf = (int)(t & 1);
-            tc_mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
-            __syncwarp();                                          // tcgen05.ld is warp-collective
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            uint32_t m[4];
-#pragma unroll
-            for (int cb = 0; cb < 4; cb++) m[cb] = tc_ld_mask(lane_base + (uint32_t)(buf * 2 * TC_ROWS + cb * 32), thr32);
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);        // the tensor core may overwrite this buffer now
-            const int64_t tile = r_begin + t * TC_ROWS;
-            // candidates of all lanes are processed in lock step, each lane in increasing row order
-            while (__any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0)) {
-                int64_t row = -1;
-#pragma unroll
-                for (int cb = 0; cb < 4; cb++) {
-                    if (row < 0 && m[cb]) {
-                        const int j = __ffs(m[cb]) - 1;
-                        m[cb] &= m[cb] - 1;
-                        row = tile + cb * 32 + j;
-                    }
-                }
-                if (row < 0 || row >= r_end) continue;
+        // Candidates wait in a small per-thread ring in shared memory and are re-scored in lock step, one per lane
+        // and round: a round costs the same whether 1 or 32 lanes have work (it is bound by the latency of the
+        // float64 row loads), so the ring is drained only when some lane has TC_FIFO_TRIGGER entries, which fills
+        // the rounds.  Each lane sees its rows in increasing order.
+        int f_head = 0, f_cnt = 0, wpos = 0;
+        int32_t *fifo = s_fifo + ql;
+        auto drain = [&]() {
+            while (__any_sync(0xffffffffu, f_cnt > 0)) {
+                if (f_cnt == 0) continue;
+                const int64_t row = fifo[(size_t)(f_head & (TC_FIFO - 1)) * TC_QT];
+                f_head++;
+                f_cnt--;
                 const double *d = p.dbn + (size_t)row * dim;
                 double s = 0.0;
                 if (DIM > 0) {
@@ -246,23 +309,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                     }
                     for (; c < dim; c++) s = fma(qrow[c], d[c], s);
                 }
+                if (s < gthr) continue;                            // below another split's k-th score
                 if (cnt == k && !(s > thr)) continue;              // ties with the current worst keep the lower index
-                int pos = cnt < k ? cnt : k - 1;
-                while (pos > 0 && ls[(size_t)(pos - 1) * TC_QT] < s) {
-                    ls[(size_t)pos * TC_QT] = ls[(size_t)(pos - 1) * TC_QT];
-                    li[(size_t)pos * TC_QT] = li[(size_t)(pos - 1) * TC_QT];
-                    pos--;
-                }
+                // the list is unordered while it runs: overwrite the worst entry, then find the new worst with k
+                // independent loads (a sorted insert would be a dependent load-compare-store chain per position)
+                const int pos = cnt < k ? cnt : wpos;
                 ls[(size_t)pos * TC_QT] = s;
                 li[(size_t)pos * TC_QT] = (int32_t)row;
                 if (cnt < k) cnt++;
                 if (cnt == k) {
-                    thr = ls[(size_t)(k - 1) * TC_QT];
-                    thr32 = __double2float_rd(thr - TC_EPS);
+                    double w = INFINITY;
+                    int32_t wi = -1;
+                    int wp = 0;
+#pragma unroll 4
+                    for (int e = 0; e < k; e++) {
+                        const double v = ls[(size_t)e * TC_QT];
+                        const int32_t vi = li[(size_t)e * TC_QT];
+                        if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
+                    }
+                    thr = w;
+                    wpos = wp;
+                    if (gslot && thr > gthr) atomicMax(gslot, tc_enc(thr));
                 }
             }
+        };
+        // queue the rows flagged in m (block order = row order); drains when a ring is full or 'force'
+        auto enqueue = [&](uint32_t (&m)[4], int64_t tile, bool force) {
+            for (;;) {
+#pragma unroll
+                for (int cb = 0; cb < 4; cb++) {
+                    while (m[cb] && f_cnt < TC_FIFO) {
+                        const int j = __ffs(m[cb]) - 1;
+                        m[cb] &= m[cb] - 1;
+                        const int64_t row = tile + cb * 32 + j;
+                        if (row < r_end) {
+                            fifo[(size_t)((f_head + f_cnt) & (TC_FIFO - 1)) * TC_QT] = (int32_t)row;
+                            f_cnt++;
+                        }
+                    }
+                }
+                const bool more = __any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0);
+                if (more || force || __any_sync(0xffffffffu, f_cnt >= TC_FIFO_TRIGGER)) drain();
+                if (!more) break;
+            }
+        };
+        auto filter_threshold = [&]() -> float {
+            if (!active) return INFINITY;
+            const double eff = cnt == k ? fmax(thr, gthr) : gthr;
+            return eff == -INFINITY ? -INFINITY : __double2float_rd(eff - TC_EPS);
+        };
+        if (gslot) genc = __ldcg(gslot);                           // what earlier CTAs of this query already reached
+#ifdef DSPX_TC_PROFILE
+        long long tc_prof_local[16] = {0};
+#endif
+        TC_PROF_T0();
+        for (int64_t t = 0; t < n_tiles; t++) {
+            const int buf = (int)(t & 1);
+            const int64_t tile = r_begin + t * TC_ROWS;
+            tc_mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+            TC_PROF_ADD(5);
+            __syncwarp();                                          // tcgen05.ld is warp-collective
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (genc) gthr = tc_dec(genc);
+            const uint32_t acc = lane_base + (uint32_t)(buf * 2 * TC_ROWS);
+            uint32_t m[4] = {0u, 0u, 0u, 0u};
+            if (t == 0) {
+                // the list is empty: take the first tile 32 columns at a time so the threshold tightens as it fills
+#pragma unroll
+                for (int cb = 0; cb < 3; cb++) {
+                    m[cb] = tc_ld_mask(acc + cb * 32, filter_threshold());
+                    enqueue(m, tile, true);
+                }
+                m[3] = tc_ld_mask(acc + 96, filter_threshold());
+            } else {
+                const float thr32 = filter_threshold();
+                tc_ld_mask2(acc, thr32, m[0], m[1]);
+                tc_ld_mask2(acc + 64, thr32, m[2], m[3]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);        // the tensor core may overwrite this buffer now
+            if (gslot) genc = __ldcg(gslot);                       // for the next tile: in flight during the re-scoring below
+            TC_PROF_ADD(6);
+            enqueue(m, tile, t < 4 || t == n_tiles - 1);
+            TC_PROF_ADD(7);
         }
+#ifdef DSPX_TC_PROFILE
+        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { for (int i = 5; i < 8; i++) tc_prof[i] = tc_prof_local[i]; tc_prof[8] = n_tiles; }
+#endif
         if (active) {
+            // order the list once: score descending, ties to the lower index (selection sort in place)
+            for (int a = 0; a + 1 < cnt; a++) {
+                int best = a;
+                double bs = ls[(size_t)a * TC_QT];
+                int32_t bi = li[(size_t)a * TC_QT];
+                for (int e = a + 1; e < cnt; e++) {
+                    const double v = ls[(size_t)e * TC_QT];
+                    const int32_t vi = li[(size_t)e * TC_QT];
+                    if (v > bs || (v == bs && vi < bi)) { bs = v; bi = vi; best = e; }
+                }
+                if (best != a) {
+                    ls[(size_t)best * TC_QT] = ls[(size_t)a * TC_QT];
+                    li[(size_t)best * TC_QT] = li[(size_t)a * TC_QT];
+                    ls[(size_t)a * TC_QT] = bs;
+                    li[(size_t)a * TC_QT] = bi;
+                }
+            }
             const size_t o = ((size_t)gq * p.n_splits + split) * k;
             for (int e = 0; e < k; e++) {
                 const bool have = e < cnt;
@@ -272,27 +424,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         }
     } else if (tid < TC_EPI_THREADS + TC_PROD_THREADS) {
         // ===== producers: database tile -> hi / lo operand tiles =====
+        // A tile is 16 KB and a load takes ~1 us to return: every thread keeps its 16 float4 of the NEXT tile in
+        // flight while it waits for the stage to be released (Little's law: less than a tile in flight starves
+        // the tensor core).
         const int ptid = tid - TC_EPI_THREADS;
+        constexpr int PER = TC_ROWS * 8 / TC_PROD_THREADS;         // 16 chunks of 16 bytes per thread
+        float4 v[PER];
+        auto fetch = [&](int64_t t) {
+            const float4 *src = reinterpret_cast<const float4 *>(pp.dbf + (size_t)(r_begin + t * TC_ROWS) * TC_KPAD);
+#pragma unroll
+            for (int i = 0; i < PER; i++) v[i] = __ldg(src + ptid + i * TC_PROD_THREADS);
+        };
+        if (n_tiles > 0) fetch(0);
+#ifdef DSPX_TC_PROFILE
+        long long tc_prof_local[16] = {0};
+#endif
+        TC_PROF_T0();
         for (int64_t t = 0; t < n_tiles; t++) {
             const int s = (int)(t % TC_STAGES);
             tc_mbar_wait(&empty_b[s], (uint32_t)(((t / TC_STAGES) & 1) ^ 1));
-            const float *src = pp.dbf + (size_t)(r_begin + t * TC_ROWS) * TC_KPAD;
+            TC_PROF_ADD(3);
             unsigned char *hi = b_hi + s * TC_ROWS * 128, *lo = b_lo + s * TC_ROWS * 128;
-#pragma unroll 4
-            for (int c = ptid; c < TC_ROWS * 8; c += TC_PROD_THREADS) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + c);
-                tc_store_split(hi, lo, c >> 3, c & 7, v);
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int c = ptid + i * TC_PROD_THREADS;
+                tc_store_split(hi, lo, c >> 3, c & 7, v[i]);
             }
             asm volatile("fence.proxy.async.shared::cta;");
             tc_mbar_arrive(&full_b[s]);
+            if (t + 1 < n_tiles) fetch(t + 1);
+            TC_PROF_ADD(4);
         }
+#ifdef DSPX_TC_PROFILE
+        if (ptid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { tc_prof[3] = tc_prof_local[3]; tc_prof[4] = tc_prof_local[4]; }
+#endif
     } else if (lane == 0) {
         // ===== tensor-core issue: one thread =====
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#ifdef DSPX_TC_PROFILE
+        long long tc_prof_local[16] = {0};
+        const long long tc_start = clock64();
+#endif
+        TC_PROF_T0();
         for (int64_t t = 0; t < n_tiles; t++) {
             const int s = (int)(t % TC_STAGES), buf = (int)(t & 1);
             tc_mbar_wait(&acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
+            TC_PROF_ADD(0);
             tc_mbar_wait(&full_b[s], (uint32_t)((t / TC_STAGES) & 1));
+            TC_PROF_ADD(1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint64_t bh = tc_desc(b_hi + s * TC_ROWS * 128), bl = tc_desc(b_lo + s * TC_ROWS * 128);
 #pragma unroll
@@ -308,7 +487,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             }
             tc_commit(&empty_b[s]);                                // smem stage free once these MMAs have read it
             tc_commit(&acc_full[buf]);                             // accumulators complete
+            TC_PROF_ADD(2);
         }
+#ifdef DSPX_TC_PROFILE
+        if (blockIdx.x == 0 && blockIdx.y == 0) { for (int i = 0; i < 3; i++) tc_prof[i] = tc_prof_local[i]; tc_prof[9] = clock64() - tc_start; }
+#endif
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;");
