@@ -127,7 +127,7 @@ def main():
                               "retrieval_seconds": t_ret, "queries_per_s": n_q_total / t_ret,
                               "pair_scores_per_s": n_q_total * n_db_total / t_ret,
                               "hit_at_10": res[0][1] / res[0][2], "hit_at_20": res[1][1] / res[1][2],
-                              "retrieval_includes": "all-gather of DB embeddings (NCCL), FP64 scoring, top-20, hit@k, all-reduce",
+                              "retrieval_includes": "all-gather of DB embeddings (NCCL), tensor-core filter + exact FP64 re-score, top-20, hit@k, all-reduce",
                               "oracle_parity": parity}), flush=True)
     if world > 1:
         dist.destroy_process_group()
