@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--kernel", default="auto", choices=("auto", "generic", "warp8"))
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--stft-steps", type=int, default=10, help="secondary stft() measurement (0 = skip)")
+    ap.add_argument("--retrieval-steps", type=int, default=3, help="secondary cosine top-20 measurement (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -65,6 +66,17 @@ def measured_peaks() -> tuple[float, str]:
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+def measured_tensor_peak() -> tuple[float, str]:
+    """Dense bf16 TFLOP/s (MEASURED_PEAKS.json, burst figure; nominal 2250 otherwise)."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["bf16_tflops"]), "measured"
+        except Exception:
+            pass
+    return 2250.0, "fallback"
 
 
 def host_cores() -> int:
@@ -286,6 +298,45 @@ def run_ours(args) -> None:
         stft_sel = s_out[[0, b - 1]][:, [0, 1, n_frames - 1]].cpu().numpy()
         del s_out
 
+    # secondary: MFCC-embedding retrieval (src/retrieval/retrieval.py): top-20 of 20 000 queries against 1 000 000
+    # database embeddings of dimension 26 per GPU (synthetic unit-variance embeddings), through dspx_cosine_topk
+    retrieval_info = None
+    if args.retrieval_steps > 0:
+        from dsp_final_b200 import retrieval as R
+
+        RQ, RDB, RDIM, RK = 20_000, 1_000_000, 26, 20
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(77 + rank)
+        r_q = torch.randn((RQ, RDIM), generator=gen, device=dev)
+        r_db = torch.randn((RDB, RDIM), generator=gen, device=dev)
+        r_idx = R.cosine_topk(r_q, r_db, RK)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(args.retrieval_steps):
+            r_idx = R.cosine_topk(r_q, r_db, RK)
+        r1.record(stream)
+        barrier()
+        r_ms = r0.elapsed_time(r1) / args.retrieval_steps
+        tt = torch.tensor([r_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        r_ms = float(tt.item())
+        bf16_peak, tpeak_src = measured_tensor_peak()
+        tf32_peak = bf16_peak / 2.0                                 # TF32 runs at half the dense bf16 rate
+        useful = 2.0 * RDIM * RQ * RDB / (r_ms * 1e-3) / 1e12
+        retrieval_info = {"value": world * RQ / (r_ms * 1e-3), "unit": "queries/s", "ms_per_step": r_ms,
+                          "pair_scores_per_s": world * RQ * RDB / (r_ms * 1e-3), "n_queries": RQ, "n_db": RDB, "dim": RDIM, "k": RK,
+                          "roofline": {"bound": "tensor", "achieved": useful, "peak": tf32_peak, "unit": "TFLOP/s",
+                                       "frac": useful / tf32_peak, "peak_source": tpeak_src + " bf16 / 2", "executed_tflops": useful * 192.0 / 52.0,
+                                       "note": "achieved = 2*dim flop per pair (what the path needs); the kernel executes "
+                                               "3 split-TF32 passes of K = 32 (192 flop per pair) plus float64 re-scoring"},
+                          "kernel": "cosine_topk_tc (tcgen05 TF32 filter + exact float64 re-score)", "steps": args.retrieval_steps}
+        r_sel_q = r_q[:8].cpu().numpy()
+        r_sel_idx = r_idx[:8].cpu().numpy()
+        r_db_host = r_db.cpu().numpy() if rank == 0 else None
+        del r_q, r_db, r_idx
+
     # end to end through the host-buffer C ABI: pinned host clips in, host features out
     e2e = None
     if args.e2e_steps > 0:
@@ -365,6 +416,9 @@ def run_ours(args) -> None:
     if stft_info is not None:
         ref_st = np.stack([O.stft(clips[i].cpu().numpy(), FL, HOP)[[0, 1, n_frames - 1]] for i in (0, b - 1)])
         parity["stft_rel_err"] = O.relative_error(stft_sel, ref_st)
+    if retrieval_info is not None:
+        parity["retrieval_top20_identical"] = bool(np.array_equal(r_sel_idx, O.cosine_topk(r_sel_q, r_db_host, 20)))
+        parity["retrieval_queries_checked"] = 8
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
@@ -389,7 +443,7 @@ def run_ours(args) -> None:
                                f"{N_MELS} mels, {N_MFCC} MFCC (BASELINE.json configs[1])",
                    "outputs": args.outputs, "clips_per_gpu": b, "kernel": plan.kernel,
                    "l2_policy": "inputs_larger_than_l2 (1.76 GB per pass vs 126 MB L2)", "parallelism": f"clip-sharded x{world}"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps, "stft": stft_info,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps, "stft": stft_info, "retrieval": retrieval_info,
         "clocks": clocks, "parity": parity,
     }
     print(json.dumps(line), flush=True)

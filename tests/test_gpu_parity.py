@@ -307,6 +307,25 @@ def test_retrieval_float32_collisions(torch_cuda, dim, k):
     assert np.array_equal(sc, want_sc)
 
 
+def test_retrieval_duplicates_across_splits(torch_cuda):
+    """A large database is ranked in several splits that share a pruning threshold: copies of the same row spread
+    over the whole index range must come back lowest index first, for every supported k of the filter kernels."""
+    from dsp_final_b200 import retrieval as R
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(99)
+    nq, ndb, dim = 300, 150_000, 26
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    db = rng.standard_normal((ndb, dim)).astype(np.float32)
+    for c in range(20):                                    # 48 copies of a near-query row, one every ~3000 rows
+        db[rng.integers(0, 3000) + np.arange(48) * 3100] = q[c] * 1.5 + 0.01 * rng.standard_normal(dim).astype(np.float32)
+    for k in (1, 20, 28, 33):
+        idx, sc = R.cosine_topk(q, db, k, return_scores=True)
+        want_idx, want_sc = O.cosine_topk(q, db, k, return_scores=True)
+        assert np.array_equal(idx, want_idx), k
+        assert np.array_equal(sc, want_sc), k
+
+
 def test_retrieval_sweep_config3(torch_cuda):
     """BASELINE.json configs[2] in miniature: frame x hop sweep, fold-5 queries vs folds 1-4,
     identical index lists and identical Top-10 / Top-20 against the oracle on the same embeddings."""
