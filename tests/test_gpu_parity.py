@@ -308,8 +308,9 @@ def test_retrieval_float32_collisions(torch_cuda, dim, k):
 
 
 def test_retrieval_duplicates_across_splits(torch_cuda):
-    """A large database is ranked in several splits that share a pruning threshold: copies of the same row spread
-    over the whole index range must come back lowest index first, for every supported k of the filter kernels."""
+    """A large database is ranked in several splits that share a pruning threshold.  Copies of one row spread over
+    the whole index range must come back lowest index first; a block of more identical rows than the filter kernel
+    keeps per list (k + 8) must be detected and those queries re-ranked by the all-float64 kernel."""
     from dsp_final_b200 import retrieval as R
     from oracle import oracle as O
 
@@ -317,13 +318,22 @@ def test_retrieval_duplicates_across_splits(torch_cuda):
     nq, ndb, dim = 300, 150_000, 26
     q = rng.standard_normal((nq, dim)).astype(np.float32)
     db = rng.standard_normal((ndb, dim)).astype(np.float32)
-    for c in range(20):                                    # 48 copies of a near-query row, one every ~3000 rows
+    for c in range(20):                                    # queries 0-19: 48 copies of a near-query row, one every ~3100 rows
         db[rng.integers(0, 3000) + np.arange(48) * 3100] = q[c] * 1.5 + 0.01 * rng.standard_normal(dim).astype(np.float32)
-    for k in (1, 20, 28, 33):
-        idx, sc = R.cosine_topk(q, db, k, return_scores=True)
+    for c in range(20, 30):                                # queries 20-29: 64 copies in one contiguous block
+        start = 5000 + (c - 20) * 14_000
+        db[start:start + 64] = q[c] * 0.7 + 0.01 * rng.standard_normal(dim).astype(np.float32)
+    for k in (1, 20, 24, 28, 33):
+        st = {}
+        idx, sc = R.cosine_topk(q, db, k, return_scores=True, stats=st)
         want_idx, want_sc = O.cosine_topk(q, db, k, return_scores=True)
         assert np.array_equal(idx, want_idx), k
         assert np.array_equal(sc, want_sc), k
+        # k <= 24 takes the filter path: exactly the ten block queries cannot be proven complete
+        assert st["reranked"] == (10 if k <= 24 else 0), (k, st)
+    st = {}
+    R.cosine_topk(q[30:], db, 20, stats=st)                 # no query sits on a cluster: the filter alone suffices
+    assert st["reranked"] == 0, st
 
 
 def test_retrieval_sweep_config3(torch_cuda):
