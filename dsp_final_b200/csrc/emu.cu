@@ -184,6 +184,8 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     while (reinterpret_cast<uintptr_t>(ws) & 15) ws++;
     w8_carve(blob.data(), ws, tb, p.n_mels, c);
     c.alpha = p.alpha;
+    c.win_a = cfg->window == DSPX_WINDOW_HANN ? 0.25f : (cfg->window == DSPX_WINDOW_HAMMING ? 0.27f : 0.5f);
+    c.win_b = cfg->window == DSPX_WINDOW_HANN ? -0.25f : (cfg->window == DSPX_WINDOW_HAMMING ? -0.23f : 0.f);
     c.n_mels = p.n_mels;
     c.n_mfcc = p.n_mfcc;
     c.rounds = tb.rounds;
@@ -191,15 +193,17 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     const int r1 = tb.r1;
     const int units = r1 >= 8 ? r1 / 8 : 1;
     std::vector<W8Power> pw(32 * 2);
+    // the device kernel computes window / twiddles on the feature path and loads them in STFT mode: replay the same
+#define W8_P1(R, PRE_, SH_) do { if (p.stft) w8_pass1<R, PRE_, SH_, false>(c, lane); else w8_pass1<R, PRE_, SH_, true>(c, lane); } while (0)
     for (uint32_t item = 0; item < p.n_items; item++) {
         w8_set_item(p, c, item);
         for (int lane = 0; lane < 32; lane++) {
             const bool share = 2 * cfg->hop_length == e.P && r1 != 16;
-            if (r1 == 4 && share) { if (pre) w8_pass1<4, true, true>(c, lane); else w8_pass1<4, false, true>(c, lane); }
-            else if (r1 == 4) { if (pre) w8_pass1<4, true, false>(c, lane); else w8_pass1<4, false, false>(c, lane); }
-            else if (r1 == 8 && share) { if (pre) w8_pass1<8, true, true>(c, lane); else w8_pass1<8, false, true>(c, lane); }
-            else if (r1 == 8) { if (pre) w8_pass1<8, true, false>(c, lane); else w8_pass1<8, false, false>(c, lane); }
-            else { if (pre) w8_pass1<16, true, false>(c, lane); else w8_pass1<16, false, false>(c, lane); }
+            if (r1 == 4 && share) { if (pre) W8_P1(4, true, true); else W8_P1(4, false, true); }
+            else if (r1 == 4) { if (pre) W8_P1(4, true, false); else W8_P1(4, false, false); }
+            else if (r1 == 8 && share) { if (pre) W8_P1(8, true, true); else W8_P1(8, false, true); }
+            else if (r1 == 8) { if (pre) W8_P1(8, true, false); else W8_P1(8, false, false); }
+            else { if (pre) w8_pass1<16, true, false, false>(c, lane); else w8_pass1<16, false, false, false>(c, lane); }
         }
         for (int lane = 0; lane < 32; lane++) {
             if (r1 == 4) w8_pass2<4>(c, lane);

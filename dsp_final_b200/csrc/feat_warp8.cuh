@@ -194,6 +194,7 @@ struct W8Params {
     uint32_t pairs_per_clip, n_items;
     int hop, n_mels, n_mfcc, prefetch, share;
     float alpha;
+    float win_a, win_b;      // see W8Ctx
     W8Tables tb;
     const float *tables;     // global copy of the blob
     float *logmel, *mfcc;    // either may be null
@@ -213,6 +214,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     const float *fa, *fb;    // first sample of frame A / frame B
     int firstA, firstB;      // frame starts at sample 0 of its clip (no predecessor for pre-emphasis)
     float alpha;
+    float win_a, win_b;      // 0.5 w[n] = win_a + win_b cos(2 pi n / P): hann (0.25, -0.25), hamming (0.27, -0.23), rect (0.5, 0)
     int n_mels, n_mfcc, rounds, cw_lanes, validB;
     float *logmelA, *logmelB, *mfccA, *mfccB;   // rows of the two frames (null when not requested)
     int64_t lm_fs;
@@ -251,10 +253,66 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
     c.dsc = c.lm + n_mels;
 }
 
+// ---- window and first-pass twiddles without table loads (R1 <= 8) ---------------------------------------
+// Both are functions of one angle per thread: u = exp(-2 pi i tid / M) (the k_a = 1 twiddle, one 8-byte load).
+// Twiddles are its powers (depth-3 product tree); the window of row a, sample i is
+// win_a + win_b cos(phi_i + 2 pi a / R1) with cos phi_0 = Re u, sin phi_0 = -Im u and phi_1 = phi_0 + 2 pi / P.
+// The shared-memory pipe is the kernel's bottleneck; these ~90 FP32 instructions per frame pair replace 60 of its
+// wavefronts (+5 % measured).  Rounding differs from the tables by a few 1e-7 (tolerance 1e-4).
+DSPX_HD float2 w8_cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
+
+template <int R1> struct W8Trig {
+    float2 C, S, D, E;                                 // (cos, sin)(phi_0 | phi_1) packed, and (C -+ S) / sqrt 2
+    float2 u[R1 - 1];                                  // u^1 .. u^(R1-1)
+    DSPX_HD explicit W8Trig(float2 u1)
+    {
+        constexpr float dc = R1 == 4 ? 0.99992470183914450299f : 0.99998117528260110909f;    // cos(2 pi / P), P = 128 R1
+        constexpr float ds = R1 == 4 ? 0.01227153828571992608f : 0.00613588464915447536f;    // sin(2 pi / P)
+        const float c0 = u1.x, s0 = -u1.y;
+        C = make_float2(c0, fmaf(c0, dc, -s0 * ds));
+        S = make_float2(s0, fmaf(s0, dc, c0 * ds));
+        if constexpr (R1 == 8) {
+            const float2 h = bc2(0.70710678118654752440f);
+            D = mul2(sub2(C, S), h);
+            E = mul2(add2(C, S), h);
+        }
+        u[0] = u1;
+        u[1] = w8_cmul(u1, u1);
+        u[2] = w8_cmul(u[1], u1);
+        if constexpr (R1 == 8) {
+            u[3] = w8_cmul(u[1], u[1]);
+            u[4] = w8_cmul(u[3], u1);
+            u[5] = w8_cmul(u[3], u[1]);
+            u[6] = w8_cmul(u[3], u[2]);
+        }
+    }
+    // (0.5 w[n], 0.5 w[n + 1]) for n = 128 a + 2 tid: cos(phi + 2 pi a / R1) is one of +-C, +-S, +-D, +-E
+    DSPX_HD float2 window(int a, float wa, float wb) const
+    {
+        const int k = a * (8 / R1);                    // eighth-root index
+        const float2 v = (k == 0 || k == 4) ? C : (k == 2 || k == 6) ? S : (k == 1 || k == 5) ? D : E;
+        const bool neg = k == 2 || k == 3 || k == 4 || k == 5;      // cos(phi + k pi/4): C, D, -S, -E, -C, -D, S, E
+        return fma2(v, bc2(neg ? -wb : wb), bc2(wa));
+    }
+};
+
+template <int R1, bool TRIG, class Trig> DSPX_HD float2 w8_window_of(const W8Ctx &c, const Trig &t, int s, int a, int lane)
+{
+    if (TRIG) return t.window(a, c.win_a, c.win_b);
+    return c.win[(s * R1 + a) * 32 + lane];
+}
+template <int R1, bool TRIG, class Trig> DSPX_HD float2 w8_twiddle_of(const W8Ctx &c, const Trig &t, int s, int ka, int lane)
+{
+    if (TRIG) return t.u[(ka - 1) % 7];
+    return c.tw1[(s * (R1 - 1) + ka - 1) * 32 + lane];
+}
+
 // ---- phase A: load, pre-emphasis, window, radix-R1 over a, twiddle, store -----------------
 // All loads of a set are issued before the first use (memory-level parallelism); the only
 // sample without a predecessor is sample 0 of a clip (y[0] = x[0], src/dsp/mfcc.py:88).
-template <int R1, bool PRE, bool SHARE>
+// TRIG: window and twiddles computed (feature path, R1 <= 8) instead of loaded (STFT mode is HBM-bound and keeps
+// the loads: the extra instructions cost it 2 %; R1 = 16 has no registers to spare)
+template <int R1, bool PRE, bool SHARE, bool TRIG>
 DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 {
     if (SHARE) {
@@ -292,10 +350,11 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
                     y0[r] = DSPX_FSUB_RN(x[r].x, DSPX_FMUL_RN(c.alpha, pv[r]));
                 }
             }
+            const W8Trig<(R1 <= 8 ? R1 : 8)> trig(c.tw1[(s * (R1 - 1)) * 32 + lane]);      // dead code unless TRIG
             float2 re[R1], im[R1];
 #pragma unroll
             for (int a = 0; a < R1; a++) {
-                const float2 w = c.win[(s * R1 + a) * 32 + lane];       // (0.5 w[n], 0.5 w[n+1])
+                const float2 w = w8_window_of<R1, TRIG>(c, trig, s, a, lane);    // (0.5 w[n], 0.5 w[n+1])
                 re[a] = mul2(make_float2(y0[a], y0[a + SH]), bc2(w.x));
                 im[a] = mul2(make_float2(y1[a], y1[a + SH]), bc2(w.y));
             }
@@ -303,7 +362,7 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
             c.xbuf[w8_addr(0, tid >> 3, tid & 7)] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
 #pragma unroll
             for (int ka = 1; ka < R1; ka++) {
-                const float2 w = c.tw1[(s * (R1 - 1) + ka - 1) * 32 + lane];
+                const float2 w = w8_twiddle_of<R1, TRIG>(c, trig, s, ka, lane);
                 cmul2(re[ka], im[ka], w.x, w.y);
                 c.xbuf[w8_addr(ka, tid >> 3, tid & 7)] = make_float4(re[ka].x, re[ka].y, im[ka].x, im[ka].y);
             }
@@ -333,6 +392,7 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
                 pvb[a] = pb[128 * a - 1];
             }
         }
+        const W8Trig<(R1 <= 8 ? R1 : 8)> trig(c.tw1[(s * (R1 - 1)) * 32 + lane]);      // unused (and dropped) for R1 = 16
         float2 re[R1], im[R1];
 #pragma unroll
         for (int a = 0; a < R1; a++) {
@@ -343,7 +403,7 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
                 y1 = sub2(y1, t1);                                                          // ... rounded differences
                 y0 = sub2(y0, t0);
             }
-            const float2 w = c.win[(s * R1 + a) * 32 + lane];           // (0.5 w[n], 0.5 w[n+1])
+            const float2 w = w8_window_of<R1, TRIG>(c, trig, s, a, lane);       // (0.5 w[n], 0.5 w[n+1])
             re[a] = mul2(y0, bc2(w.x));
             im[a] = mul2(y1, bc2(w.y));
         }
@@ -351,7 +411,7 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
         c.xbuf[w8_addr(0, tid >> 3, tid & 7)] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
 #pragma unroll
         for (int ka = 1; ka < R1; ka++) {
-            const float2 w = c.tw1[(s * (R1 - 1) + ka - 1) * 32 + lane];  // exp(-2 pi i tid ka / M)
+            const float2 w = w8_twiddle_of<R1, TRIG>(c, trig, s, ka, lane);     // exp(-2 pi i tid ka / M)
             cmul2(re[ka], im[ka], w.x, w.y);
             c.xbuf[w8_addr(ka, tid >> 3, tid & 7)] = make_float4(re[ka].x, re[ka].y, im[ka].x, im[ka].y);
         }
@@ -680,6 +740,8 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     W8Ctx c;
     w8_carve(w8_smem, w8_smem + p.tb.total + warp * wf, p.tb, p.n_mels, c);
     c.alpha = p.alpha;
+    c.win_a = p.win_a;
+    c.win_b = p.win_b;
     c.n_mels = p.n_mels;
     c.n_mfcc = p.n_mfcc;
     c.rounds = p.tb.rounds;
@@ -687,7 +749,7 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     const uint32_t n_warps = gridDim.x * NW;
     for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
-        w8_pass1<R1, PRE, SHARE>(c, lane);
+        w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8)>(c, lane);
         if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
         w8_pass2<R1>(c, lane);
@@ -960,6 +1022,8 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.prefetch = 1;
     p.share = (2 * pl->cfg.hop_length == pl->P) && !getenv("DSPX_W8_NOSHARE");
     p.alpha = (float)pl->cfg.pre_emphasis;
+    p.win_a = pl->cfg.window == DSPX_WINDOW_HANN ? 0.25f : (pl->cfg.window == DSPX_WINDOW_HAMMING ? 0.27f : 0.5f);
+    p.win_b = pl->cfg.window == DSPX_WINDOW_HANN ? -0.25f : (pl->cfg.window == DSPX_WINDOW_HAMMING ? -0.23f : 0.f);
     p.tb = pd->tb;
     p.tables = static_cast<const float *>(pl->d_fast_tables);
     p.logmel = logmel;
