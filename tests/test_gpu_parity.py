@@ -336,6 +336,49 @@ def test_retrieval_duplicates_across_splits(torch_cuda):
     assert st["reranked"] == 0, st
 
 
+def test_retrieval_fuzz_filter_kernels(torch_cuda):
+    """Randomised shapes and adversarial score distributions through the tensor-core filter path (dim <= 32,
+    k <= 24) and its float64 fallback: indices and scores must equal the oracle's bit for bit every time."""
+    from dsp_final_b200 import retrieval as R
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(20260)
+    kinds = ("normal", "clustered", "negative", "duplicates", "all_same", "zeros", "tiny_scale")
+    for case in range(42):
+        kind = kinds[case % len(kinds)]
+        dim = int(rng.choice([1, 2, 5, 13, 26, 31, 32]))
+        ndb = int(rng.choice([1, 7, 24, 127, 128, 129, 1000, 4097, 33_000]))
+        nq = int(rng.choice([1, 3, 255, 256, 257, 600]))
+        k = int(min(ndb, rng.choice([1, 2, 10, 20, 24])))
+        q = rng.standard_normal((nq, dim))
+        db = rng.standard_normal((ndb, dim))
+        if kind == "clustered":                            # every cosine close to 1 (like raw MFCC statistics)
+            base = rng.standard_normal(dim) * 5.0
+            q = base + 0.01 * q
+            db = base + 0.01 * db
+        elif kind == "negative":                           # all similarities negative
+            base = np.abs(rng.standard_normal(dim)) + 0.5
+            q = base + 0.05 * q
+            db = -base + 0.05 * db
+        elif kind == "duplicates" and ndb > 4:
+            src = rng.integers(0, ndb, size=ndb // 2)
+            db[rng.integers(0, ndb, size=ndb // 2)] = db[src]
+        elif kind == "all_same":
+            db[:] = db[0]
+        elif kind == "zeros":
+            db[rng.integers(0, ndb, size=max(1, ndb // 3))] = 0.0
+            q[0] = 0.0
+        elif kind == "tiny_scale":
+            q *= 1e-12
+            db *= 1e12
+        dt = np.float32 if case % 2 else np.float64
+        q, db = q.astype(dt), db.astype(dt)
+        idx, sc = R.cosine_topk(q, db, k, return_scores=True)
+        want_idx, want_sc = O.cosine_topk(q, db, k, return_scores=True)
+        assert np.array_equal(idx, want_idx), (case, kind, nq, ndb, dim, k)
+        assert np.array_equal(sc, want_sc), (case, kind, nq, ndb, dim, k)
+
+
 def test_retrieval_sweep_config3(torch_cuda):
     """BASELINE.json configs[2] in miniature: frame x hop sweep, fold-5 queries vs folds 1-4,
     identical index lists and identical Top-10 / Top-20 against the oracle on the same embeddings."""
