@@ -323,22 +323,17 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
         for (int s = 0; s < 2; s++) {
             const int tid = lane + 32 * s;
             const float *pa = c.fa + 2 * tid;
+            const float *ph = c.validB ? pa : pa - 128 * SH;             // no frame B: rows >= R1 replay frame A's rows
             float2 x[NR];
             float pv[NR];
 #pragma unroll
-            for (int r = 0; r < NR; r++) {
-                const int rr = (r >= R1 && !c.validB) ? r - SH : r;      // no frame B: replay frame A's rows
-                x[r] = *reinterpret_cast<const float2 *>(pa + 128 * rr);
-            }
+            for (int r = 0; r < NR; r++) x[r] = *reinterpret_cast<const float2 *>((r >= R1 ? ph : pa) + 128 * r);
             if (PRE) {
                 const bool edge = c.firstA && tid == 0;
                 pv[0] = *(edge ? pa : pa - 1);
                 if (edge) pv[0] = 0.f;
 #pragma unroll
-                for (int r = 1; r < NR; r++) {
-                    const int rr = (r >= R1 && !c.validB) ? r - SH : r;
-                    pv[r] = pa[128 * rr - 1];
-                }
+                for (int r = 1; r < NR; r++) pv[r] = (r >= R1 ? ph : pa)[128 * r - 1];
             }
             float y0[NR], y1[NR];
 #pragma unroll
