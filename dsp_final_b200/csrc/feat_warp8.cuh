@@ -660,12 +660,29 @@ DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
 // so a warp load touches one row per part: conflict-free.  Parts are combined through dsc[].
 DSPX_HD void w8_dct_partial(const W8Ctx &c, int lane, int c0)
 {
-    const int cwl = c.cw_lanes, parts = 32 / cwl;
-    const int q = lane & (cwl - 1), part = lane / cwl;
-    const float *col = c.dct + (size_t)(c0 / cwl) * c.n_mels * cwl + q;     // block-major table
-    float2 acc = make_float2(0.f, 0.f);
-    for (int f = part; f < c.n_mels; f += parts) acc = fma2(c.lm[f], bc2(col[f * cwl]), acc);
-    c.dsc[lane] = acc;
+    // cw_lanes is 16 or 32: shifts instead of divisions, pointer steps instead of index products, four loads per trip
+    const int sh = c.cw_lanes == 16 ? 4 : 5;
+    const int parts = 32 >> sh;                                             // 2 or 1; parts * cw_lanes == 32
+    const int q = lane & (c.cw_lanes - 1), part = lane >> sh;
+    const float *col = c.dct + (size_t)c0 * c.n_mels + q + (part << sh);    // block-major table, row `part`
+    const float2 *lm = c.lm + part;
+    const int n = (c.n_mels - part + parts - 1) >> (5 - sh);               // rows part, part + parts, ...
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        acc0 = fma2(lm[0], bc2(col[0]), acc0);
+        acc1 = fma2(lm[parts], bc2(col[32]), acc1);
+        acc0 = fma2(lm[2 * parts], bc2(col[64]), acc0);
+        acc1 = fma2(lm[3 * parts], bc2(col[96]), acc1);
+        lm += 4 * parts;
+        col += 128;
+    }
+    for (; i < n; i++) {
+        acc0 = fma2(lm[0], bc2(col[0]), acc0);
+        lm += parts;
+        col += 32;
+    }
+    c.dsc[lane] = add2(acc0, acc1);
 }
 
 DSPX_HD void w8_dct_store(const W8Ctx &c, int lane, int c0)
