@@ -210,7 +210,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     const int4 *fdesc;
     const float *dct;
     float4 *xbuf;
-    float2 *pbuf, *seg_a, *seg_b, *lm, *dsc;
+    float2 *pbuf, *seg, *lm, *dsc;
     const float *fa, *fb;    // first sample of frame A / frame B
     int firstA, firstB;      // frame starts at sample 0 of its clip (no predecessor for pre-emphasis)
     float alpha;
@@ -247,9 +247,8 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
     c.dct = tables_smem + tb.dct;
     c.xbuf = reinterpret_cast<float4 *>(warp_smem);
     c.pbuf = reinterpret_cast<float2 *>(warp_smem);
-    c.seg_a = c.pbuf + (W8_CSTRIDE * tb.n_slots + 16);
-    c.seg_b = c.seg_a + tb.n_segs;
-    c.lm = c.seg_b + tb.n_segs;
+    c.seg = c.pbuf + (W8_CSTRIDE * tb.n_slots + 16);          // 2 n_segs sums in filter order + one dump slot
+    c.lm = c.seg + 2 * tb.n_segs + 2;
     c.dsc = c.lm + n_mels;
 }
 
@@ -598,7 +597,7 @@ DSPX_HD void w8_store_power(const W8Ctx &c, int lane, int w, const W8Power &pw)
 // Every bin k feeds (at most) filter g(k) with weight a_k and filter g(k)+1 with weight b_k
 // (csrc/tables.cuh "bin view").  Runs of equal g are cut into chunks of 8 bins; lane l walks
 // chunks l*R .. l*R+R-1, accumulating in registers while the run continues and dropping one
-// (sum a P, sum b P) segment per run piece.  Chunks are 64 B apart in the tile, so chunk parity picks
+// (sum a P, sum b P) pair per run piece, each sum at the slot where its filter will read it.  Chunks are 64 B apart in the tile, so chunk parity picks
 // the half of a 128-byte line and the lane reads its four 16-byte pieces rotated by (lane >> 1) & 3:
 // the 128-bit loads of 8 neighbouring lanes hit 8 different bank groups (rounds is odd, so parity
 // alternates with the lane).  The weight rows (80 B apart) are stored pre-rotated to match.
@@ -607,7 +606,7 @@ DSPX_HD void w8_mel_chunks(const W8Ctx &c, int lane)
     float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
     for (int r = 0; r < c.rounds; r++) {
         const int ch = lane * c.rounds + r;
-        const int flag = c.cflag[ch];                                   // bit0 first, bit1 last, >>8 segment
+        const int flag = c.cflag[ch];                                   // bit0 first, bit1 last, 8..19 / 20..31 slots of the sums
         const float4 *pp = reinterpret_cast<const float4 *>(c.pbuf + ch * W8_CSTRIDE);
         const float4 *ww = reinterpret_cast<const float4 *>(c.cw + ch * W8_WROW);
         float2 ca = make_float2(0.f, 0.f), cb = make_float2(0.f, 0.f);
@@ -623,8 +622,8 @@ DSPX_HD void w8_mel_chunks(const W8Ctx &c, int lane)
         if (flag & 1) { sa = ca; sb = cb; }
         else { sa = add2(sa, ca); sb = add2(sb, cb); }
         if (flag & 2) {
-            c.seg_a[flag >> 8] = sa;
-            c.seg_b[flag >> 8] = sb;
+            c.seg[(flag >> 8) & 0xfff] = sa;
+            c.seg[(unsigned)flag >> 20] = sb;
         }
     }
 }
@@ -642,10 +641,10 @@ DSPX_HD float w8_log(float x)
 DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
 {
     for (int f = lane; f < c.n_mels; f += 32) {
-        const int4 d = c.fdesc[f];                                     // {a first, a count, b first, b count}
+        const int4 d = c.fdesc[f];                                     // {first, count}: the sums of a filter are contiguous
+        const float2 *sp = c.seg + d.x;
         float2 s = make_float2(0.f, 0.f);
-        for (int i = 0; i < d.y; i++) s = add2(s, c.seg_a[d.x + i]);
-        for (int i = 0; i < d.w; i++) s = add2(s, c.seg_b[d.z + i]);
+        for (int i = 0; i < d.y; i++) s = add2(s, sp[i]);
         const float2 v = make_float2(w8_log(fmaxf(s.x, 1e-10f)), w8_log(fmaxf(s.y, 1e-10f)));
         c.lm[f] = v;
         if (c.logmelA) {
@@ -896,7 +895,25 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         if (last) { seg_cnt[ch.run]++; seg++; }
     }
     tb.n_segs = std::max(seg, 1);
-    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16 + 2 * tb.n_segs + n_mels + 32)) + 16;
+    // slots of the sums: filter g reads [b sums of run g-1][a sums of run g] as one contiguous range
+    std::vector<int> run_of_filter(n_mels + 1, -1);
+    for (int r = 0; r < n_runs; r++)
+        if (run_g[r] >= 0 && run_g[r] <= n_mels) run_of_filter[run_g[r]] = r;
+    std::vector<int> slot_a(tb.n_segs, 2 * tb.n_segs), slot_b(tb.n_segs, 2 * tb.n_segs);      // default: dump slot
+    std::vector<int> f_first(n_mels, 0), f_cnt(n_mels, 0);
+    int slot = 0;
+    for (int g = 0; g < n_mels; g++) {
+        f_first[g] = slot;
+        const int rb = g >= 1 ? run_of_filter[g - 1] : -1, ra = run_of_filter[g];
+        if (rb >= 0) for (int i = 0; i < seg_cnt[rb]; i++) slot_b[seg_first[rb] + i] = slot++;
+        if (ra >= 0) for (int i = 0; i < seg_cnt[ra]; i++) slot_a[seg_first[ra] + i] = slot++;
+        f_cnt[g] = slot - f_first[g];
+    }
+    for (int ci = 0; ci < n_chunks; ci++) {
+        const int sg = cflag[ci] >> 8;
+        cflag[ci] = (cflag[ci] & 3) | (slot_a[sg] << 8) | (int32_t)((uint32_t)slot_b[sg] << 20);
+    }
+    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16 + 2 * tb.n_segs + 2 + n_mels + 32)) + 16;
     int32_t *ppos = reinterpret_cast<int32_t *>(blob.data() + tb.ppos);
     for (int w = 0; w < units; w++)
         for (int m = 0; m < 9; m++)
@@ -907,14 +924,9 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
                 ppos[((w * 9 + m) * 32 + l) * 2 + 1] = pos[M - k];
             }
     int32_t *fdesc = reinterpret_cast<int32_t *>(blob.data() + tb.fdesc);
-    for (int r = 0; r < n_runs; r++) {
-        const int g = run_g[r];
-        fdesc[4 * g] = seg_first[r];                       // filter g collects the "a" sums of run g ...
-        fdesc[4 * g + 1] = seg_cnt[r];
-        if (g + 1 < n_mels) {                              // ... and filter g+1 the "b" sums
-            fdesc[4 * (g + 1) + 2] = seg_first[r];
-            fdesc[4 * (g + 1) + 3] = seg_cnt[r];
-        }
+    for (int g = 0; g < n_mels; g++) {
+        fdesc[4 * g] = f_first[g];
+        fdesc[4 * g + 1] = f_cnt[g];
     }
     // DCT table, block-major: [block][filter][cw_lanes], zero beyond n_mfcc
     for (int b = 0; b < dct_blocks; b++)

@@ -110,6 +110,13 @@ inline void build_filterbank(int n_mels, int n_fft, int sr, double f_min, double
             t.two_band_ok = false;
         }
     }
+    // the warp8 kernel walks runs of equal bin_filt and expects one run per filter: the index must not decrease
+    int prev = -1;
+    for (int k = 0; k < bins; k++) {
+        if (t.bin_filt[k] < 0) continue;
+        if (t.bin_filt[k] < prev) t.two_band_ok = false;
+        prev = t.bin_filt[k];
+    }
 }
 
 inline void build_dct2(int n_mfcc, int n_mels, std::vector<double> &d)
