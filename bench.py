@@ -330,8 +330,8 @@ def run_ours(args) -> None:
                           "roofline": {"bound": "tensor", "achieved": useful, "peak": tf32_peak, "unit": "TFLOP/s",
                                        "frac": useful / tf32_peak, "peak_source": tpeak_src + " bf16 / 2", "executed_tflops": useful * 192.0 / 52.0,
                                        "note": "achieved = 2*dim flop per pair (what the path needs); the kernel executes "
-                                               "3 split-TF32 passes of K = 32 (192 flop per pair); float64 only for the k + 8 kept rows per split"},
-                          "kernel": "cosine_topk_tc (tcgen05 TF32 candidate filter) + topk_tc_finalize (exact float64 re-score)", "steps": args.retrieval_steps}
+                                               "3 split-TF32 passes of K = 32 (192 flop per pair) plus float64 re-scoring of the rows that pass"},
+                          "kernel": "cosine_topk_tc (tcgen05 TF32 filter + exact float64 re-score)", "steps": args.retrieval_steps}
         r_sel_q = r_q[:8].cpu().numpy()
         r_sel_idx = r_idx[:8].cpu().numpy()
         r_db_host = r_db.cpu().numpy() if rank == 0 else None

@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -175,6 +177,28 @@ int main()
         printf("-- unit vectors, spread %g\n", spread);
         run(false, A, B, 1.0);
         rc |= run(true, A, B, 2e-6);
+    }
+    // adversarial mantissas: every value has its 13 low bits set (largest possible residual, all of one sign), so the
+    // dropped lo * lo terms and the truncation of the lo operands add up instead of cancelling
+    for (int trial = 0; trial < 2; trial++) {
+        auto fill = [&](std::vector<float> &X, int rows) {
+            for (int r = 0; r < rows; r++) {
+                double nrm = 0, t[32];
+                for (int c = 0; c < 26; c++) { t[c] = 1.0 + (trial ? 0.3 : 0.001) * ((rand() % 20001 - 10000) / 10000.0); nrm += t[c] * t[c]; }
+                for (int c = 0; c < 32; c++) {
+                    float v = c < 26 ? (float)(t[c] / sqrt(nrm)) : 0.f;
+                    uint32_t b;
+                    memcpy(&b, &v, 4);
+                    if (c < 26) b |= 0x1fffu;
+                    memcpy(&v, &b, 4);
+                    X[r * K + c] = v;
+                }
+            }
+        };
+        fill(A, M);
+        fill(B, N);
+        printf("-- adversarial low mantissa bits, trial %d\n", trial);
+        rc |= run(true, A, B, 8e-6);
     }
     return rc;
 }

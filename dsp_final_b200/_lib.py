@@ -81,7 +81,6 @@ _SIGNATURES = {
     "dspx_next_pow_two": (_I64, [_I64]),
     "dspx_fft_c2c": (_I32, [_VP, _I64, _I64, _I64, _I32, _VP, _VP, _VP]),
     "dspx_cosine_topk_workspace": (_SZ, [_I64, _I64, _I32, _I32]),
-    "dspx_cosine_topk_reranked": (_I64, [_VP, _I64, _I64, _I32, _I32]),
     "dspx_cosine_topk": (_I32, [_VP, _I64, _VP, _I64, _I32, _I32, _I32, _VP, _VP, _VP, _SZ, _VP]),
     "dspx_cosine_matrix": (_I32, [_VP, _I64, _VP, _I64, _I32, _I32, _VP, _VP, _SZ, _VP]),
     "dspx_dct2": (_I32, [_VP, _I64, _I32, _I32, _VP, _VP]),

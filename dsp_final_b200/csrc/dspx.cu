@@ -723,33 +723,7 @@ size_t dspx_cosine_topk_workspace(int64_t nq, int64_t ndb, int dim, int k)
     b += align256((size_t)((nq + TC_QT - 1) / TC_QT) * TC_QT * TC_KPAD * 4);
     b += align256((size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4);
     b += align256((size_t)nq * 8);                                                // thresholds shared between splits
-    // tensor-core filter: kept rows and their scores per (query, split), re-rank flags, flag counter
-    b += 2 * align256((size_t)nq * TC_MAX_SPLITS * (TC_MAX_K + TC_MARGIN) * 4) + align256((size_t)nq) + 256;
     return b + 1024;
-}
-
-// byte offset of the re-rank counter inside the workspace (the layout dspx_cosine_topk carves below)
-static size_t topk_counter_offset(int64_t nq, int64_t ndb, int dim, int k)
-{
-    size_t o = align256((size_t)nq * dim * 8) + align256((size_t)ndb * dim * 8);
-    o += align256((size_t)nq * TK_MAX_SPLITS * k * 8) + align256((size_t)nq * TK_MAX_SPLITS * k * 4);
-    o += align256((size_t)((nq + TC_QT - 1) / TC_QT) * TC_QT * TC_KPAD * 4);
-    o += align256((size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4);
-    o += align256((size_t)nq * 8);
-    o += 2 * align256((size_t)nq * TC_MAX_SPLITS * (TC_MAX_K + TC_MARGIN) * 4) + align256((size_t)nq);
-    return o;
-}
-
-int64_t dspx_cosine_topk_reranked(const void *workspace_dev, int64_t nq, int64_t ndb, int dim, int k)
-{
-    if (!workspace_dev || nq < 0 || ndb < 0 || dim <= 0 || k <= 0) return -1;
-    unsigned int n = 0;
-    const char *p = static_cast<const char *>(workspace_dev) + topk_counter_offset(nq, ndb, dim, k);
-    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&n, p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
-        set_error("dspx_cosine_topk_reranked: %s", cudaGetErrorString(cudaGetLastError()));
-        return -1;
-    }
-    return (int64_t)n;
 }
 
 int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t ndb, int dim, int dtype, int k,
@@ -782,21 +756,7 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     float *dbf_t = reinterpret_cast<float *>(ws);
     const size_t dbf_bytes = (size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4;
     ws += align256(dbf_bytes);
-    unsigned int *shared_thr = reinterpret_cast<unsigned int *>(ws);
-    ws += align256((size_t)nq * 8);
-    const size_t cand_bytes = align256((size_t)nq * TC_MAX_SPLITS * (TC_MAX_K + TC_MARGIN) * 4);
-    int32_t *cand_idx = reinterpret_cast<int32_t *>(ws);
-    ws += cand_bytes;
-    float *cand_score = reinterpret_cast<float *>(ws);
-    ws += cand_bytes;
-    unsigned char *rerank = reinterpret_cast<unsigned char *>(ws);
-    ws += align256((size_t)nq);
-    unsigned int *n_rerank = reinterpret_cast<unsigned int *>(ws);
-    if (reinterpret_cast<char *>(n_rerank) != static_cast<char *>(workspace_dev) + topk_counter_offset(nq, ndb, dim, k)) {
-        set_error("internal: workspace layout mismatch");
-        return DSPX_EINVAL;
-    }
-    DSPX_CUDA_CHECK(cudaMemsetAsync(n_rerank, 0, 4, st));
+    unsigned long long *shared_thr = reinterpret_cast<unsigned long long *>(ws);
     // Filter kernels (single-chunk dimensions, lists that fit beside the tiles), all with exact float64 re-scoring:
     // tensor-core TF32 filter, else packed-FP32 filter, else the all-float64 kernel.  DSPX_TOPK = tc | f32 | f64 forces one.
     const char *force = getenv("DSPX_TOPK");
@@ -876,52 +836,21 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
         tp.idx_out = tp.n_splits == 1 ? idx_out_dev : pidx;
         tp.score_out = tp.n_splits == 1 ? score_out_dev : pscore;
         if (use_tc) {
-            if (tp.n_splits > TC_MAX_SPLITS) { set_error("internal: too many splits for the filter kernel"); return DSPX_EINVAL; }
             TopkTcParams cp{};
             cp.base = tp;
             cp.qf = qf_t;
             cp.dbf = dbf_t;
-            cp.kp = k + TC_MARGIN;
-            cp.cand_idx = cand_idx;
-            cp.cand_score = cand_score;
             cp.shared_thr = tp.n_splits > 1 ? shared_thr : nullptr;
-            if (cp.shared_thr) DSPX_CUDA_CHECK(cudaMemsetAsync(shared_thr, 0, (size_t)nq * 4, st));
+            if (cp.shared_thr) DSPX_CUDA_CHECK(cudaMemsetAsync(shared_thr, 0, (size_t)nq * 8, st));
             dim3 cgrid((unsigned)qtiles, (unsigned)tp.n_splits);
-            const size_t smem = topk_tc_smem_bytes(cp.kp);
-            DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)topk_tc_smem_bytes(TC_MAX_K + TC_MARGIN)));
-            cosine_topk_tc_kernel<<<cgrid, TC_THREADS, smem, st>>>(cp);
-            DSPX_CUDA_CHECK(cudaGetLastError());
-            // exact float64 re-score and order of the kept rows; flags the queries whose lists may be incomplete
-            topk_tc_finalize_kernel<<<(unsigned)((nq + TC_FIN_WARPS - 1) / TC_FIN_WARPS), TC_FIN_WARPS * 32, 0, st>>>(
-                cand_idx, cand_score, tp.n_splits, cp.kp, qn, dbn, nq, dim, k, idx_out_dev, score_out_dev, rerank, n_rerank);
-            DSPX_CUDA_CHECK(cudaGetLastError());
-            // ... and those (normally none: the CTAs exit at once) go through the all-float64 kernel
-            TopkParams fb = tp;
-            fb.only = rerank;
-            fb.n_splits = topk_splits(nq, ndb, sm);
-            int64_t frps = (ndb + fb.n_splits - 1) / fb.n_splits;
-            frps = (frps + TK_ROWS - 1) / TK_ROWS * TK_ROWS;
-            fb.rows_per_split = frps;
-            fb.n_splits = (int)((ndb + frps - 1) / frps);
-            fb.idx_out = fb.n_splits == 1 ? idx_out_dev : pidx;
-            fb.score_out = fb.n_splits == 1 ? score_out_dev : pscore;
-            dim3 fgrid64((unsigned)((nq + TK_QPC - 1) / TK_QPC), (unsigned)fb.n_splits);
+            const size_t smem = topk_tc_smem_bytes(k);
             if (dim == 26) {
-                const size_t fsmem = topk_smem_bytes(dim, k, 26);
-                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                cosine_topk_kernel<26><<<fgrid64, TK_WARPS * 32, fsmem, st>>>(fb);
+                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_tc_smem_bytes(TC_MAX_K)));
+                cosine_topk_tc_kernel<26><<<cgrid, TC_THREADS, smem, st>>>(cp);
             } else {
-                const size_t fsmem = topk_smem_bytes(dim, k, 32);
-                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                cosine_topk_kernel<32><<<fgrid64, TK_WARPS * 32, fsmem, st>>>(fb);
+                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_tc_smem_bytes(TC_MAX_K)));
+                cosine_topk_tc_kernel<0><<<cgrid, TC_THREADS, smem, st>>>(cp);
             }
-            DSPX_CUDA_CHECK(cudaGetLastError());
-            if (fb.n_splits > 1) {
-                topk_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(pidx, pscore, nq, fb.n_splits, k, idx_out_dev, score_out_dev, rerank);
-                DSPX_CUDA_CHECK(cudaGetLastError());
-            }
-            return DSPX_OK;
         } else {
         TopkF32Params fp{};
         fp.base = tp;

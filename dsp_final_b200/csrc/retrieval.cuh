@@ -93,7 +93,6 @@ struct TopkParams {
     int64_t rows_per_split; // multiple of TK_ROWS
     int32_t *idx_out;       // n_splits == 1: [nq, k]; else partial [nq, n_splits, k]
     double *score_out;      // same shape (may be null only when n_splits == 1)
-    const unsigned char *only;   // optional [nq] flags: rank only the flagged queries (re-run after the filter kernel)
 };
 
 // Insert (cs, ci) into the sorted list of one query (descending score; equal scores keep
@@ -238,11 +237,6 @@ __global__ void __launch_bounds__(TK_WARPS * 32, 2) cosine_topk_kernel(const Top
         tk_cp_commit();
     };
 
-    if (p.only) {                                                      // nothing flagged in this tile of queries: done
-        int any = 0;
-        for (int i = tid; i < TK_QPC; i += TK_WARPS * 32) any |= (q0 + i < p.nq) && p.only[q0 + i];
-        if (!__syncthreads_or(any)) return;
-    }
     int cnt[TK_QPW];
     double thr[TK_QPW];
 #pragma unroll
@@ -303,7 +297,7 @@ __global__ void __launch_bounds__(TK_WARPS * 32, 2) cosine_topk_kernel(const Top
     for (int qi = 0; qi < TK_QPW; qi++) {
         const int ql = warp * TK_QPW + qi;
         const int64_t gq = q0 + ql;
-        if (gq >= p.nq || (p.only && !p.only[gq])) continue;
+        if (gq >= p.nq) continue;
         const double *ls = s_ls + (size_t)ql * p.k;
         const int32_t *li = s_li + (size_t)ql * p.k;
         const size_t o = ((size_t)gq * p.n_splits + split) * p.k;
@@ -323,12 +317,11 @@ inline size_t topk_smem_bytes(int dim, int k, int cw)
 
 // merge the per-split sorted lists of one query (one warp per query, one list per lane)
 __global__ void __launch_bounds__(128) topk_merge_kernel(const int32_t *pidx, const double *pscore, int64_t nq,
-                                                        int n_splits, int k, int32_t *idx_out, double *score_out,
-                                                        const unsigned char *only = nullptr)
+                                                        int n_splits, int k, int32_t *idx_out, double *score_out)
 {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= nq || (only && !only[q])) return;
+    if (q >= nq) return;
     const size_t base = ((size_t)q * n_splits + lane) * k;
     int head = 0;
     for (int out = 0; out < k; out++) {

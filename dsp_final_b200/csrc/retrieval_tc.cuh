@@ -1,32 +1,29 @@
-// retrieval_tc.cuh -- exact cosine top-k with a tensor-core (tcgen05, TF32) candidate filter.
+// retrieval_tc.cuh -- exact cosine top-k with a tensor-core (tcgen05, TF32) pre-filter.
 //
 // Same contract as cosine_topk_kernel (retrieval.cuh): float64 scores accumulated left to right with fused
 // multiply-adds, descending order, ties to the lower database index -- the result is bit-identical.  The
-// similarity matrix q . db^T is a GEMM, so the 5th-generation tensor cores produce an approximate score for
-// every pair; a streaming kernel keeps, per query, the k + TC_MARGIN best rows by that score, and a second
-// small kernel re-scores only those in float64 and orders them exactly.  Replaces the argsort over the dense
-// matrix of src/retrieval/retrieval.py:25-49.
+// similarity matrix q . db^T is a GEMM, so the scores that only have to be *compared* against each query's
+// current k-th score are produced by the 5th-generation tensor cores; the few pairs that pass are re-scored
+// exactly in float64.  Replaces the argsort over the dense matrix of src/retrieval/retrieval.py:25-49.
 //
-// Arithmetic of the filter: kind::tf32 keeps 10 mantissa bits of each operand (~1e-3 on a unit-vector dot
-// product).  Each float32 value v is therefore split into hi = v with the low 13 mantissa bits cleared (exact
-// in TF32) and lo = v - hi, and the product is accumulated as A_lo B_hi + A_hi B_lo + A_hi B_hi: three K = 32
-// passes into the same float32 accumulator.  What is dropped is below 3 * 2^-20 of sum |q_i d_i| <= 1; measured
-// against float64 on unit vectors (benchmarks/micro/umma_tf32.cu) the error is 5e-7.  TC_EPS = 2e-5 bounds
-// |s_tc - s64| with a factor 40 to spare.
-//
-// Why the result is exact.  Rows are ordered by (s_tc descending, index ascending).  A member x of the true
-// top-k has s64(x) >= s64_k (the exact k-th score), hence s_tc(x) > s64_k - eps.  x can only be missing from
-// its split's list if that list is full and its worst entry t_i satisfies t_i >= s_tc(x), or if it was pruned
-// against another split's published worst entry t_j > s_tc(x).  The finalize kernel therefore checks
-// max_i t_i < s64_k - eps over the full lists: when it holds, every true member was kept and the float64
-// re-score orders them exactly; when it does not (more than TC_MARGIN rows within 2 eps of the k-th score,
-// e.g. many duplicated rows) the query is flagged and re-ranked by the all-float64 kernel.
+// Arithmetic: kind::tf32 keeps 10 mantissa bits of each operand (~1e-3 on a unit-vector dot product), which
+// would pass far too many pairs for tightly clustered embeddings.  Each float32 value v is therefore split
+// into hi = v with the low 13 mantissa bits cleared (exact in TF32) and lo = v - hi, and the product is
+// accumulated as A_lo B_hi + A_hi B_lo + A_hi B_hi: three K = 32 passes into the same float32 accumulator.
+// What is dropped is A_lo B_lo and the truncation of the lo operands to TF32, each below 2^-20 |q_i d_i|, i.e.
+// 2.9e-6 in total since sum |q_i d_i| <= 1 for unit vectors; rounding the inputs to float32 adds 1.2e-7 and twelve
+// float32 accumulator roundings at most 1.4e-6: 4.5e-6 worst case.  Measured against float64
+// (benchmarks/micro/umma_tf32.cu): 5e-7 on random and clustered unit vectors, 1.2e-6 with adversarial mantissas
+// (all 13 low bits set, all residuals of one sign).  TC_EPS = 8e-6, so every pair with s64 >= thr64 has
+// s_tc > thr32 = float(thr64 - eps) and is re-scored.  eps only costs extra re-scores: on tightly clustered
+// embeddings (every cosine near 1, thousands of rows within eps of the k-th score) the kernel degrades towards the
+// all-float64 kernel's time instead of failing.
 //
 // Structure of a CTA (352 threads, one per SM), 256 queries x one database split:
-//   warps 0-7  epilogue: thread = one query.  tcgen05.ld its accumulator row, compare with the thread's
-//              threshold (3-input max tree over 32 columns, bit mask only on a hit), release the TMEM buffer,
-//              queue (row, score) in a per-query ring and insert queued pairs into the thread's own unordered
-//              list in shared memory (overwrite the worst entry, rescan for the new worst).  No float64 here.
+//   warps 0-7  epilogue: thread = one query.  tcgen05.ld its accumulator row (32 columns at a time), compare
+//              with the thread's threshold, release the TMEM buffer, then re-score the candidates in float64
+//              and insert them into the thread's own sorted list in shared memory (rows arrive in index
+//              order, so "strictly better than the current worst" keeps ties at the lower index).
 //   warps 8-9  producers: database tile (128 rows x 32 floats, zero padded) from global memory, split into
 //              hi / lo, stored K-major under the 128-byte swizzle the tensor core expects; mbarrier hand-off.
 //   warp 10    one lane issues 2 x 12 tcgen05.mma (M 128, N 128, K 8) per tile into a double-buffered
@@ -45,11 +42,9 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_EPI_THREADS = 256, TC_PROD_THREADS = 64;
 constexpr int TC_THREADS = TC_EPI_THREADS + TC_PROD_THREADS + 32;
 constexpr int TC_KPAD = 32;           // floats per row of the padded float copies (one 128-byte swizzle row)
-constexpr double TC_EPS = 2e-5;
+constexpr double TC_EPS = 8e-6;
 constexpr int TC_FIFO = 8, TC_FIFO_TRIGGER = 4;   // pending candidates per query: ring size / drain trigger
-constexpr int TC_MARGIN = 8;          // extra list entries beyond k kept by the approximate score
-constexpr int TC_MAX_K = 24;          // the per-thread lists ([k + margin][256] float + int) share smem with the tiles
-constexpr int TC_MAX_SPLITS = 16;
+constexpr int TC_MAX_K = 28;          // the per-thread lists ([k][256] doubles + ints) share smem with the tiles
 
 template <typename T>
 __global__ void normalize_rows_pad32_kernel(const T *x, int64_t n, int dim, double *out64, float *out32)
@@ -83,27 +78,22 @@ __device__ long long tc_prof[16];
 #endif
 
 struct TopkTcParams {
-    TopkParams base;        // idx_out / score_out unused here: the lists go to cand_idx / cand_score
+    TopkParams base;
     const float *qf;        // [ceil(nq / 256) * 256][32], zero padded
     const float *dbf;       // [ceil(ndb / 128) * 128][32], zero padded
-    unsigned int *shared_thr;   // [nq] order-encoded worst list scores shared by the splits of a query (null: one split)
-    int kp;                 // list length: k + TC_MARGIN
-    int32_t *cand_idx;      // [nq][n_splits][kp] rows kept (-1: empty), unordered
-    float *cand_score;      // [nq][n_splits][kp] their tensor-core scores
+    unsigned long long *shared_thr;   // [nq] order-encoded k-th scores shared by the splits of a query (null: one split)
 };
 
-// order-preserving float <-> uint32 (0 is below every float): lets atomicMax maintain a shared threshold
-__device__ __forceinline__ unsigned int tc_enc(float f)
+// order-preserving double <-> uint64 (0 is below every double): lets atomicMax maintain a shared threshold
+__device__ __forceinline__ unsigned long long tc_enc(double d)
 {
-    const unsigned int b = __float_as_uint(f);
-    return (b >> 31) ? ~b : (b | 0x80000000u);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-__device__ __forceinline__ float tc_dec(unsigned int u)
+__device__ __forceinline__ double tc_dec(unsigned long long u)
 {
-    return __uint_as_float((u >> 31) ? (u & 0x7fffffffu) : ~u);
+    return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
 }
-// largest float below f (f finite)
-__device__ __forceinline__ float tc_below(float f) { return tc_dec(tc_enc(f) - 1u); }
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -157,8 +147,27 @@ __device__ __forceinline__ void tc_store_split(unsigned char *hi_tile, unsigned 
     *reinterpret_cast<float4 *>(lo_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 
-// 32 accumulator columns of this thread's TMEM lane: issue, and wait.  The wait names the destination registers as
-// in/out operands so that no use of them can be scheduled above it.
+// 32 accumulator columns of this thread's TMEM lane -> bit j set when column j passes the threshold
+__device__ __forceinline__ uint32_t tc_ld_mask(uint32_t taddr, float thr32)
+{
+    uint32_t v[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) m |= (__uint_as_float(v[j]) > thr32) ? (1u << j) : 0u;
+    return m;
+}
+
+// Issue / wait split of the same load: the wait names the destination registers as in/out operands so that no use of
+// them can be scheduled above it.  With two register buffers the load of block i + 1 is in flight while block i is scanned.
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -179,30 +188,33 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&v)[32])
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :: "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
+// Bit j set when column j passes the threshold.  Almost every block of 32 columns is entirely below it: a max tree
+// (3-input FMNMX, log depth) decides that in 16 instructions; the mask is only built when some lane of the warp has a hit.
+__device__ __forceinline__ uint32_t tc_mask32(const uint32_t (&w)[32], float thr32)
 {
-    tc_ld32_issue(taddr, v);
-    tc_ld_wait(v);
-}
-// v[j] for a run-time j: five levels of selects (register arrays cannot be indexed dynamically)
-__device__ __forceinline__ float tc_pick(const uint32_t *w, int j)
-{
-    uint32_t a[16], b[8], c[4];
+    float mx[11];
 #pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = (j & 1) ? w[2 * i + 1] : w[2 * i];
+    for (int j = 0; j < 10; j++)
+        mx[j] = fmaxf(fmaxf(__uint_as_float(w[3 * j]), __uint_as_float(w[3 * j + 1])), __uint_as_float(w[3 * j + 2]));
+    mx[10] = fmaxf(__uint_as_float(w[30]), __uint_as_float(w[31]));
+    const float t0 = fmaxf(fmaxf(mx[0], mx[1]), mx[2]), t1 = fmaxf(fmaxf(mx[3], mx[4]), mx[5]);
+    const float t2 = fmaxf(fmaxf(mx[6], mx[7]), mx[8]), t3 = fmaxf(mx[9], mx[10]);
+    const float top = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+    if (!__any_sync(0xffffffffu, top > thr32)) return 0u;
+    uint32_t part[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int i = 0; i < 8; i++) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
-    const uint32_t d0 = (j & 8) ? c[1] : c[0], d1 = (j & 8) ? c[3] : c[2];
-    return __uint_as_float((j & 16) ? d1 : d0);
-}
-
-inline size_t topk_tc_smem_bytes(int kp)
-{
-    return (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * kp * 8 + (size_t)TC_FIFO * TC_QT * 8 + 128;
+    for (int j = 0; j < 32; j++) part[j & 3] |= (__uint_as_float(w[j]) > thr32) ? (1u << j) : 0u;
+    return (part[0] | part[1]) | (part[2] | part[3]);
 }
 
+inline size_t topk_tc_smem_bytes(int k)
+{
+    return (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 4 + 128;
+}
+
+// DIM > 0: the embedding dimension is a compile-time constant (all loads of the exact dot product in flight at
+// once); DIM == 0: any dim <= 32.
+template <int DIM>
 __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const TopkTcParams pp)
 {
     const TopkParams &p = pp.base;
@@ -212,15 +224,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     unsigned char *a_lo = a_hi + 2 * TC_ROWS * 128;
     unsigned char *b_hi = a_lo + 2 * TC_ROWS * 128;               // [TC_STAGES][128 x 128 B]
     unsigned char *b_lo = b_hi + TC_STAGES * TC_ROWS * 128;
-    float *s_ls = reinterpret_cast<float *>(b_lo + TC_STAGES * TC_ROWS * 128);       // [kp][256] list scores
-    int32_t *s_li = reinterpret_cast<int32_t *>(s_ls + (size_t)pp.kp * TC_QT);       // [kp][256] list rows
-    float *s_fs = reinterpret_cast<float *>(s_li + (size_t)pp.kp * TC_QT);           // [TC_FIFO][256] pending scores
-    int32_t *s_fi = reinterpret_cast<int32_t *>(s_fs + TC_FIFO * TC_QT);             // [TC_FIFO][256] pending rows
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_fi + TC_FIFO * TC_QT);           // 8-byte aligned (all sizes are multiples of 1 KB)
+    double *s_ls = reinterpret_cast<double *>(b_lo + TC_STAGES * TC_ROWS * 128);     // [k][256]
+    int32_t *s_li = reinterpret_cast<int32_t *>(s_ls + (size_t)p.k * TC_QT);         // [k][256]
+    int32_t *s_fifo = s_li + (size_t)p.k * TC_QT;                                    // [TC_FIFO][256] pending candidate rows
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_fifo + TC_FIFO * TC_QT);         // 8-byte aligned
     uint64_t *full_b = bars, *empty_b = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dim = DIM > 0 ? DIM : p.dim;
     const int64_t q0 = (int64_t)blockIdx.x * TC_QT;
     const int split = blockIdx.y;
     const int64_t r_begin = (int64_t)split * p.rows_per_split;    // multiple of TC_ROWS
@@ -254,156 +266,179 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         const int ql = tid;                                        // = (warp >> 2) * 128 + (warp & 3) * 32 + lane
         const int64_t gq = q0 + ql;
         const bool active = gq < p.nq;
-        float *ls = s_ls + ql;                                     // entry e at ls[e * TC_QT]
+        const double *qrow = p.qn + (size_t)(active ? gq : 0) * dim;
+        double *ls = s_ls + ql;                                    // element e at ls[e * TC_QT]
         int32_t *li = s_li + ql;
-        float *fs = s_fs + ql;
-        int32_t *fi = s_fi + ql;
-        const int kp = pp.kp;
-        int cnt = 0, wpos = 0;                                     // list fill, position of its worst entry
-        float thr = -INFINITY;                                     // score of the worst entry once the list is full
-        int f_head = 0, f_cnt = 0;
-        // Splits of one query share the best "worst kept score" any of them has reached: a row scoring below it is
-        // beaten by k + margin rows of that split and can be skipped.  This only prunes work.
-        unsigned int *gslot = (pp.shared_thr && active) ? pp.shared_thr + gq : nullptr;
-        float gthr = -INFINITY;
-        unsigned int genc = 0;
-#ifdef DSPX_TC_PROFILE
-        long long tc_prof_local[16] = {0};
-#endif
-        // pending (row, score) pairs -> list.  Rows arrive in increasing order, so a pair that ties the worst
-        // entry loses (strict >), and the worst entry is the lowest score with the highest row.
+        const int k = p.k;
+        int cnt = 0;
+        double thr = 0.0;                                          // k-th score of this thread's list once it is full
+        // Splits of one query share the best k-th score any of them has reached (gthr): a row scoring below it
+        // can never enter the merged top-k, so it is neither re-scored nor inserted.  This only prunes work --
+        // every member of the final top-k scores >= gthr at all times and is among the k best of its own split.
+        unsigned long long *gslot = (pp.shared_thr && active) ? pp.shared_thr + gq : nullptr;
+        double gthr = -INFINITY;
+        unsigned long long genc = 0;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TC_ROWS);
+        // Candidates wait in a small per-thread ring in shared memory and are re-scored in lock step, one per lane
+        // and round: a round costs the same whether 1 or 32 lanes have work (it is bound by the latency of the
+        // float64 row loads), so the ring is drained only when some lane has TC_FIFO_TRIGGER entries, which fills
+        // the rounds.  Each lane sees its rows in increasing order.
+        int f_head = 0, f_cnt = 0, wpos = 0;
+        int32_t *fifo = s_fifo + ql;
         auto drain = [&]() {
             while (__any_sync(0xffffffffu, f_cnt > 0)) {
                 if (f_cnt == 0) continue;
-                const int slot = f_head & (TC_FIFO - 1);
-                const float s = fs[(size_t)slot * TC_QT];
-                const int32_t row = fi[(size_t)slot * TC_QT];
+                const int64_t row = fifo[(size_t)(f_head & (TC_FIFO - 1)) * TC_QT];
                 f_head++;
                 f_cnt--;
-                if (cnt == kp && !(s > thr)) continue;
-                const int pos = cnt < kp ? cnt : wpos;
+                const double *d = p.dbn + (size_t)row * dim;
+                double s = 0.0;
+                if (DIM > 0) {
+                    double dv[DIM > 0 ? DIM : 1], qv[DIM > 0 ? DIM : 1];
+#pragma unroll
+                    for (int c = 0; c < DIM; c++) { dv[c] = d[c]; qv[c] = qrow[c]; }
+#pragma unroll
+                    for (int c = 0; c < DIM; c++) s = fma(qv[c], dv[c], s);
+                } else {
+                    int c = 0;
+                    for (; c + 8 <= dim; c += 8) {
+                        double dv[8], qv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { dv[j] = d[c + j]; qv[j] = qrow[c + j]; }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) s = fma(qv[j], dv[j], s);
+                    }
+                    for (; c < dim; c++) s = fma(qrow[c], d[c], s);
+                }
+                if (s < gthr) continue;                            // below another split's k-th score
+                if (cnt == k && !(s > thr)) continue;              // ties with the current worst keep the lower index
+                // the list is unordered while it runs: overwrite the worst entry, then find the new worst with k
+                // independent loads (a sorted insert would be a dependent load-compare-store chain per position)
+                const int pos = cnt < k ? cnt : wpos;
                 ls[(size_t)pos * TC_QT] = s;
-                li[(size_t)pos * TC_QT] = row;
-                if (cnt < kp) cnt++;
-                if (cnt == kp) {
-                    float w0 = INFINITY, w1 = INFINITY;
-                    int32_t i0 = -1, i1 = -1;
-                    int p0 = 0, p1 = 0;
+                li[(size_t)pos * TC_QT] = (int32_t)row;
+                if (cnt < k) cnt++;
+                if (cnt == k) {
+                    double w = INFINITY, w1 = INFINITY;           // two independent scans (even / odd entries)
+                    int32_t wi = -1, wi1 = -1;
+                    int wp = 0, wp1 = 0;
                     int e = 0;
-                    for (; e + 1 < kp; e += 2) {                    // two independent scans
-                        const float a = ls[(size_t)e * TC_QT], b = ls[(size_t)(e + 1) * TC_QT];
-                        const int32_t ai = li[(size_t)e * TC_QT], bi = li[(size_t)(e + 1) * TC_QT];
-                        if (a < w0 || (a == w0 && ai > i0)) { w0 = a; i0 = ai; p0 = e; }
-                        if (b < w1 || (b == w1 && bi > i1)) { w1 = b; i1 = bi; p1 = e + 1; }
+                    for (; e + 1 < k; e += 2) {
+                        const double v = ls[(size_t)e * TC_QT], v1 = ls[(size_t)(e + 1) * TC_QT];
+                        const int32_t vi = li[(size_t)e * TC_QT], vi1 = li[(size_t)(e + 1) * TC_QT];
+                        if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
+                        if (v1 < w1 || (v1 == w1 && vi1 > wi1)) { w1 = v1; wi1 = vi1; wp1 = e + 1; }
                     }
-                    if (e < kp) {
-                        const float a = ls[(size_t)e * TC_QT];
-                        const int32_t ai = li[(size_t)e * TC_QT];
-                        if (a < w0 || (a == w0 && ai > i0)) { w0 = a; i0 = ai; p0 = e; }
+                    if (e < k) {
+                        const double v = ls[(size_t)e * TC_QT];
+                        const int32_t vi = li[(size_t)e * TC_QT];
+                        if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
                     }
-                    if (w1 < w0 || (w1 == w0 && i1 > i0)) { w0 = w1; p0 = p1; }
-                    const bool rose = w0 > thr;
-                    thr = w0;
-                    wpos = p0;
-                    if (gslot && rose && thr > gthr) atomicMax(gslot, tc_enc(thr));
+                    if (w1 < w || (w1 == w && wi1 > wi)) { w = w1; wp = wp1; }
+                    thr = w;
+                    wpos = wp;
+                    if (gslot && thr > gthr) atomicMax(gslot, tc_enc(thr));
                 }
             }
         };
-        // one block of 32 accumulator columns: max tree first (almost every block is entirely below the threshold),
-        // bit mask and queueing only when some lane of the warp has a hit
-        auto scan32 = [&](const uint32_t *w, int64_t row0, float T) {
-            float mx[11];
+        // queue the rows flagged in m (block order = row order); drains when a ring is full or 'force'
+        auto enqueue = [&](uint32_t (&m)[4], int64_t tile, bool force) {
+            for (;;) {
 #pragma unroll
-            for (int j = 0; j < 10; j++)
-                mx[j] = fmaxf(fmaxf(__uint_as_float(w[3 * j]), __uint_as_float(w[3 * j + 1])), __uint_as_float(w[3 * j + 2]));
-            mx[10] = fmaxf(__uint_as_float(w[30]), __uint_as_float(w[31]));
-            const float t0 = fmaxf(fmaxf(mx[0], mx[1]), mx[2]), t1 = fmaxf(fmaxf(mx[3], mx[4]), mx[5]);
-            const float t2 = fmaxf(fmaxf(mx[6], mx[7]), mx[8]), t3 = fmaxf(mx[9], mx[10]);
-            const float top = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-            if (!__any_sync(0xffffffffu, top > T)) return;
-            uint32_t part[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int j = 0; j < 32; j++) part[j & 3] |= (__uint_as_float(w[j]) > T) ? (1u << j) : 0u;
-            uint32_t m = (part[0] | part[1]) | (part[2] | part[3]);
-            if (row0 + 32 > r_end) {                               // rows past the end of the split score 0: never candidates
-                const int64_t valid = r_end - row0;
-                m = valid <= 0 ? 0u : (m & (0xffffffffu >> (32 - (int)valid)));
-            }
-            while (__any_sync(0xffffffffu, m != 0)) {
-                if (m != 0 && f_cnt < TC_FIFO) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int slot = (f_head + f_cnt) & (TC_FIFO - 1);
-                    fs[(size_t)slot * TC_QT] = tc_pick(w, j);
-                    fi[(size_t)slot * TC_QT] = (int32_t)(row0 + j);
-                    f_cnt++;
+                for (int cb = 0; cb < 4; cb++) {
+                    while (m[cb] && f_cnt < TC_FIFO) {
+                        const int j = __ffs(m[cb]) - 1;
+                        m[cb] &= m[cb] - 1;
+                        const int64_t row = tile + cb * 32 + j;
+                        if (row < r_end) {
+                            fifo[(size_t)((f_head + f_cnt) & (TC_FIFO - 1)) * TC_QT] = (int32_t)row;
+                            f_cnt++;
+                        }
+                    }
                 }
-                if (__any_sync(0xffffffffu, m != 0 && f_cnt == TC_FIFO)) drain();
+                const bool more = __any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0);
+                if (more || force || __any_sync(0xffffffffu, f_cnt >= TC_FIFO_TRIGGER)) drain();
+                if (!more) break;
             }
         };
-        auto filter_threshold = [&]() -> float {                   // a row is a candidate when its score is > this
+        auto filter_threshold = [&]() -> float {
             if (!active) return INFINITY;
-            const float g = gthr == -INFINITY ? -INFINITY : tc_below(gthr);      // ties with another split's worst stay in
-            return cnt == kp ? fmaxf(thr, g) : g;
+            const double eff = cnt == k ? fmax(thr, gthr) : gthr;
+            return eff == -INFINITY ? -INFINITY : __double2float_rd(eff - TC_EPS);
         };
         if (gslot) genc = __ldcg(gslot);                           // what earlier CTAs of this query already reached
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TC_ROWS);
+#ifdef DSPX_TC_PROFILE
+        long long tc_prof_local[16] = {0};
+#endif
         TC_PROF_T0();
         for (int64_t t = 0; t < n_tiles; t++) {
             const int buf = (int)(t & 1);
             const int64_t tile = r_begin + t * TC_ROWS;
             tc_mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+            TC_PROF_ADD(5);
             __syncwarp();                                          // tcgen05.ld is warp-collective
             asm volatile("tcgen05.fence::after_thread_sync;");
-            TC_PROF_ADD(5);
             if (genc) gthr = tc_dec(genc);
             const uint32_t acc = lane_base + (uint32_t)(buf * 2 * TC_ROWS);
+            uint32_t m[4] = {0u, 0u, 0u, 0u};
             if (t == 0) {
                 // the list is empty: take the first tile 32 columns at a time so the threshold tightens as it fills
-#pragma unroll 1
-                for (int cb = 0; cb < 4; cb++) {
-                    uint32_t v[32];
-                    tc_ld32(acc + cb * 32, v);
-                    scan32(v, tile + cb * 32, filter_threshold());
-                    drain();
+#pragma unroll
+                for (int cb = 0; cb < 3; cb++) {
+                    m[cb] = tc_ld_mask(acc + cb * 32, filter_threshold());
+                    enqueue(m, tile, true);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
+                m[3] = tc_ld_mask(acc + 96, filter_threshold());
             } else {
-                // two register buffers: the load of block i + 1 is in flight while block i is scanned
-                const float T = filter_threshold();
+                const float thr32 = filter_threshold();
                 uint32_t va[32], vb[32];
                 tc_ld32_issue(acc, va);
                 tc_ld_wait(va);
                 tc_ld32_issue(acc + 32, vb);
-                scan32(va, tile, T);
+                m[0] = tc_mask32(va, thr32);
                 tc_ld_wait(vb);
                 tc_ld32_issue(acc + 64, va);
-                scan32(vb, tile + 32, T);
+                m[1] = tc_mask32(vb, thr32);
                 tc_ld_wait(va);
                 tc_ld32_issue(acc + 96, vb);
-                scan32(va, tile + 64, T);
+                m[2] = tc_mask32(va, thr32);
                 tc_ld_wait(vb);
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);        // the tensor core may overwrite this buffer now
-                scan32(vb, tile + 96, T);
+                m[3] = tc_mask32(vb, thr32);
             }
-            if (gslot) genc = __ldcg(gslot);                       // for the next tile
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);        // the tensor core may overwrite this buffer now
+            if (gslot) genc = __ldcg(gslot);                       // for the next tile: in flight during the re-scoring below
             TC_PROF_ADD(6);
-            if (t < 4 || t == n_tiles - 1 || __any_sync(0xffffffffu, f_cnt >= TC_FIFO_TRIGGER)) drain();
+            enqueue(m, tile, t < 4 || t == n_tiles - 1);
             TC_PROF_ADD(7);
         }
 #ifdef DSPX_TC_PROFILE
         if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { for (int i = 5; i < 8; i++) tc_prof[i] = tc_prof_local[i]; tc_prof[8] = n_tiles; }
 #endif
         if (active) {
-            const size_t o = ((size_t)gq * p.n_splits + split) * kp;
-            for (int e = 0; e < kp; e++) {
+            // order the list once: score descending, ties to the lower index (selection sort in place)
+            for (int a = 0; a + 1 < cnt; a++) {
+                int best = a;
+                double bs = ls[(size_t)a * TC_QT];
+                int32_t bi = li[(size_t)a * TC_QT];
+                for (int e = a + 1; e < cnt; e++) {
+                    const double v = ls[(size_t)e * TC_QT];
+                    const int32_t vi = li[(size_t)e * TC_QT];
+                    if (v > bs || (v == bs && vi < bi)) { bs = v; bi = vi; best = e; }
+                }
+                if (best != a) {
+                    ls[(size_t)best * TC_QT] = ls[(size_t)a * TC_QT];
+                    li[(size_t)best * TC_QT] = li[(size_t)a * TC_QT];
+                    ls[(size_t)a * TC_QT] = bs;
+                    li[(size_t)a * TC_QT] = bi;
+                }
+            }
+            const size_t o = ((size_t)gq * p.n_splits + split) * k;
+            for (int e = 0; e < k; e++) {
                 const bool have = e < cnt;
-                pp.cand_idx[o + e] = have ? li[(size_t)e * TC_QT] : -1;
-                pp.cand_score[o + e] = have ? ls[(size_t)e * TC_QT] : -INFINITY;
+                p.idx_out[o + e] = have ? li[(size_t)e * TC_QT] : -1;
+                if (p.score_out) p.score_out[o + e] = have ? ls[(size_t)e * TC_QT] : -INFINITY;
             }
         }
     } else if (tid < TC_EPI_THREADS + TC_PROD_THREADS) {
@@ -483,106 +518,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     __syncwarp();
     if (warp == TC_THREADS / 32 - 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
-
-// ---- finalize: exact float64 re-score of the kept rows, exact order, and the safety check -----------------
-// One warp per query.  Candidates: n_splits lists of kp (row, s_tc) pairs.
-constexpr int TC_FIN_WARPS = 4;
-constexpr int TC_FIN_MAXC = TC_MAX_SPLITS * (TC_MAX_K + TC_MARGIN);
-
-__global__ void __launch_bounds__(TC_FIN_WARPS * 32) topk_tc_finalize_kernel(const int32_t *cand_idx, const float *cand_score,
-                                                                            int n_splits, int kp, const double *qn,
-                                                                            const double *dbn, int64_t nq, int dim, int k,
-                                                                            int32_t *idx_out, double *score_out,
-                                                                            unsigned char *flags, unsigned int *n_flagged)
-{
-    __shared__ double s_sc[TC_FIN_WARPS][TC_FIN_MAXC];
-    __shared__ int32_t s_ix[TC_FIN_WARPS][TC_FIN_MAXC];
-    __shared__ double s_q[TC_FIN_WARPS][32];
-    __shared__ float s_cs[TC_FIN_WARPS][TC_FIN_MAXC];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t q = (int64_t)blockIdx.x * TC_FIN_WARPS + w;
-    if (q >= nq) return;
-    const int C = n_splits * kp;
-    const int32_t *ci = cand_idx + (size_t)q * C;
-    const float *cs = cand_score + (size_t)q * C;
-    if (lane < dim) s_q[w][lane] = qn[(size_t)q * dim + lane];
-    for (int e = lane; e < C; e += 32) {                    // stage the lists: coalesced
-        s_ix[w][e] = ci[e];
-        s_cs[w][e] = cs[e];
-    }
-    __syncwarp();
-    // worst tensor-core score of every full list (lane = split)
-    float tmax = -INFINITY;
-    if (lane < n_splits) {
-        float t = INFINITY;
-        int32_t all = 0;
-        for (int e = 0; e < kp; e++) {
-            all |= s_ix[w][lane * kp + e];                  // negative (empty slot) sets the sign bit
-            t = fminf(t, s_cs[w][lane * kp + e]);
-        }
-        if (all >= 0) tmax = t;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
-    __syncwarp();
-    // A full list holds k + margin rows scoring >= tmax, so a row scoring below tmax - 2 eps is beaten exactly by
-    // at least k of them: only the rows above that line are re-scored (compacted with ballots).
-    const float keep = tmax == -INFINITY ? -INFINITY : (float)((double)tmax - 2.0 * TC_EPS) - 1e-6f;
-    int n_kept = 0;
-    for (int e0 = 0; e0 < C; e0 += 32) {
-        const int e = e0 + lane;
-        const int32_t row = e < C ? s_ix[w][e] : -1;
-        const bool take = row >= 0 && s_cs[w][e] >= keep;
-        const unsigned bal = __ballot_sync(0xffffffffu, take);   // every lane has read its entry: slots <= e may be rewritten
-        if (take) {
-            const double *d = dbn + (size_t)row * dim;
-            double dv[32];                                  // dim <= 32: all loads in flight before the chain starts
-#pragma unroll
-            for (int c = 0; c < 32; c++) dv[c] = c < dim ? d[c] : 0.0;
-            double s = 0.0;
-#pragma unroll
-            for (int c = 0; c < 32; c++)
-                if (c < dim) s = fma(s_q[w][c], dv[c], s);                 // the oracle's chain
-            const int slot = n_kept + __popc(bal & ((1u << lane) - 1u));
-            s_sc[w][slot] = s;
-            s_ix[w][slot] = row;
-        }
-        n_kept += __popc(bal);
-    }
-    __syncwarp();
-    // k rounds of arg-best under (score descending, row ascending)
-    double kth = 0.0;
-    for (int out = 0; out < k; out++) {
-        double bs = -INFINITY;
-        int32_t bi = 0x7fffffff;
-        int be = -1;
-        for (int e = lane; e < n_kept; e += 32) {
-            const double s = s_sc[w][e];
-            const int32_t i = s_ix[w][e];
-            if (i >= 0 && (s > bs || (s == bs && i < bi))) { bs = s; bi = i; be = e; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, bs, off);
-            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            const int oe = __shfl_xor_sync(0xffffffffu, be, off);
-            if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; be = oe; }
-        }
-        if (lane == 0) {
-            idx_out[(size_t)q * k + out] = be >= 0 ? bi : -1;
-            if (score_out) score_out[(size_t)q * k + out] = bs;
-            if (be >= 0) s_ix[w][be] = -1;
-        }
-        kth = bs;
-        __syncwarp();
-    }
-    if (lane == 0) {
-        const bool unsafe = (double)tmax >= kth - TC_EPS;          // a list may have dropped a member of the top-k
-        flags[q] = unsafe ? 1 : 0;
-        if (unsafe) atomicAdd(n_flagged, 1u);
-    }
-}
-
 
 #endif
 

@@ -74,13 +74,11 @@ def _dev_matrix(x):
     return t, (_lib.DTYPE_F32 if t.dtype == torch.float32 else _lib.DTYPE_F64)
 
 
-def cosine_topk(query_embeddings, db_embeddings, k: int, return_scores: bool = False, stats: dict | None = None):
+def cosine_topk(query_embeddings, db_embeddings, k: int, return_scores: bool = False):
     """Indices [nq, k] (int32) of the k most similar database rows per query, best first.
 
     NumPy in -> NumPy out; torch CUDA in -> torch CUDA out.  k is clipped to the
-    database size like the reference's slice [:, :k].  `stats`, when given, receives
-    {"reranked": queries that went through the all-float64 kernel after the tensor-core filter}
-    (this synchronises the device).
+    database size like the reference's slice [:, :k].
     """
     import torch
 
@@ -110,8 +108,6 @@ def cosine_topk(query_embeddings, db_embeddings, k: int, return_scores: bool = F
         _lib.check(lib.dspx_cosine_topk(q.data_ptr(), nq, db.data_ptr(), ndb, dim, dq, k, idx.data_ptr(),
                                         sc.data_ptr(), ws.data_ptr(), ws_bytes,
                                         torch.cuda.current_stream(dev).cuda_stream), "dspx_cosine_topk")
-        if stats is not None:
-            stats["reranked"] = int(lib.dspx_cosine_topk_reranked(ws.data_ptr(), nq, ndb, dim, k))
     if host:
         idx, sc = idx.cpu().numpy(), sc.cpu().numpy()
     return (idx, sc) if return_scores else idx

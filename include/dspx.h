@@ -161,15 +161,9 @@ int dspx_fft_c2c(const float *in_dev, int64_t batch, int64_t n_in, int64_t n, in
  * q [nq, dim], db [ndb, dim] of dtype DSPX_DTYPE_*.  Scores are float64, rows scaled by
  * 1/(||row|| + 1e-10); idx_out [nq, k] int32 in descending score order, ties broken by
  * the lower database index (np.argsort(..., kind="stable")).  score_out may be NULL.
- * workspace_dev must hold dspx_cosine_topk_workspace() bytes.  k <= DSPX_MAX_K.
- * For dim <= 32 and k <= 24 the ranking runs a tensor-core candidate filter followed by an exact float64
- * re-score (same bits as the all-float64 kernel); queries whose candidate lists cannot be proven complete
- * (many rows within 4e-5 of the k-th score, e.g. duplicated rows) are re-ranked by the float64 kernel.
- * dspx_cosine_topk_reranked() returns how many queries of the last call on this workspace took that path
- * (it synchronises the device; diagnostics only). */
+ * workspace_dev must hold dspx_cosine_topk_workspace() bytes.  k <= DSPX_MAX_K. */
 #define DSPX_MAX_K 128
 size_t dspx_cosine_topk_workspace(int64_t nq, int64_t ndb, int dim, int k);
-int64_t dspx_cosine_topk_reranked(const void *workspace_dev, int64_t nq, int64_t ndb, int dim, int k);
 int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t ndb, int dim,
                      int dtype, int k, int32_t *idx_out_dev, double *score_out_dev,
                      void *workspace_dev, size_t workspace_bytes, void *stream);
