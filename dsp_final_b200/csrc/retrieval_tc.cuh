@@ -20,10 +20,12 @@
 // all-float64 kernel's time instead of failing.
 //
 // Structure of a CTA (352 threads, one per SM), 256 queries x one database split:
-//   warps 0-7  epilogue: thread = one query.  tcgen05.ld its accumulator row (32 columns at a time), compare
-//              with the thread's threshold, release the TMEM buffer, then re-score the candidates in float64
-//              and insert them into the thread's own sorted list in shared memory (rows arrive in index
-//              order, so "strictly better than the current worst" keeps ties at the lower index).
+//   warps 0-7  epilogue: thread = one query.  tcgen05.ld its accumulator row (32 columns at a time, the next load
+//              in flight during the scan), compare with the thread's threshold (3-input max tree, bit mask only on
+//              a hit), release the TMEM buffer, queue the rows that pass in a per-query ring, and re-score queued
+//              rows in float64 in lock-step rounds into the thread's own unordered k-entry list in shared memory
+//              (overwrite the worst entry, rescan for the new worst; rows arrive in index order, so "strictly
+//              better than the current worst" keeps ties at the lower index; the list is ordered once at the end).
 //   warps 8-9  producers: database tile (128 rows x 32 floats, zero padded) from global memory, split into
 //              hi / lo, stored K-major under the 128-byte swizzle the tensor core expects; mbarrier hand-off.
 //   warp 10    one lane issues 2 x 12 tcgen05.mma (M 128, N 128, K 8) per tile into a double-buffered
