@@ -372,6 +372,28 @@ def test_retrieval_fuzz_filter_kernels(torch_cuda):
         assert np.array_equal(sc, want_sc), (case, kind, nq, ndb, dim, k)
 
 
+def test_retrieval_full_size_clustered(torch_cuda):
+    """BASELINE scale (1 M database rows) on tightly clustered, class-structured embeddings: every cosine is close to 1
+    and thousands of rows lie within the filter's epsilon of the k-th score, so the result rests entirely on the exact
+    float64 re-score.  Indices and scores must still equal the oracle's."""
+    torch = torch_cuda
+    from dsp_final_b200 import retrieval as R
+    from oracle import oracle as O
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    nq, ndb, dim, classes = 384, 1_000_000, 26, 50
+    centers = torch.randn((classes, dim), generator=g, device="cuda")
+    offset = 4.0 * torch.randn((1, dim), generator=g, device="cuda")
+    for noise in (0.02, 0.002):
+        q = offset + centers[torch.arange(nq, device="cuda") % classes] + noise * torch.randn((nq, dim), generator=g, device="cuda")
+        db = offset + centers[torch.arange(ndb, device="cuda") % classes] + noise * torch.randn((ndb, dim), generator=g, device="cuda")
+        idx, sc = R.cosine_topk(q, db, 20, return_scores=True)
+        want_idx, want_sc = O.cosine_topk(q.cpu().numpy(), db.cpu().numpy(), 20, return_scores=True)
+        assert np.array_equal(idx.cpu().numpy(), want_idx)
+        assert np.array_equal(sc.cpu().numpy(), want_sc)
+
+
 def test_retrieval_sweep_config3(torch_cuda):
     """BASELINE.json configs[2] in miniature: frame x hop sweep, fold-5 queries vs folds 1-4,
     identical index lists and identical Top-10 / Top-20 against the oracle on the same embeddings."""
