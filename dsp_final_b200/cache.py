@@ -8,9 +8,15 @@ run_retrieval.py / train_cnn.py read GPU-made features unchanged:
     <root>/<feature_type>/<sha1(params)[:12]>/fold<k>/<filename>.npy      float32 [n_frames, n_coef], C order
     <root>/<feature_type>/<digest>/manifest.json                          same keys as cache.py:96-112
 
-Format invariants kept bit for bit (cache.py:24-49, 74, 89-112): the digest recipe
-(json.dumps(params, sort_keys=True, ensure_ascii=True) with n_fft and f_max defaulted), the filename
-keeping its .wav suffix, np.save of a float32 array, atomic tmp + os.replace, manifest keys.
+What is kept is the on-disk contract, not the code (the functions below are organised around batches):
+  * digest recipe (cache.py:24-41): sha1 of json.dumps({"feature_type": ft, **params}, sort_keys=True,
+    ensure_ascii=True), first 12 hex digits.  For an MfccConfig dataclass, params = its fields with
+    n_fft None -> frame_length and f_max None -> sample_rate / 2; a plain dict (what retrieval_ml.py
+    passes for embedding_* caches) is hashed verbatim, with no defaulting;
+  * the filename keeps its ".wav" suffix, one directory per fold (cache.py:43-49);
+  * payload: np.save of a float32 C-order array, written to a unique temporary name and renamed into
+    place, so readers never see a partial file (cache.py:89-94);
+  * manifest keys and their order (cache.py:96-112).
 """
 from __future__ import annotations
 
@@ -19,64 +25,94 @@ import json
 import os
 import uuid
 from concurrent.futures import ThreadPoolExecutor
-from dataclasses import asdict, is_dataclass
+from dataclasses import fields, is_dataclass
 from datetime import datetime, timezone
 from pathlib import Path
-from typing import Any, Callable, Iterable, Sequence
+from typing import Any, Callable, Iterable, Mapping, Sequence
 
 import numpy as np
 
 FEATURE_TYPES = ("mfcc", "log_mel")
+MANIFEST_KEYS = ("feature_type", "hash", "params", "created_at", "num_files", "files")
+_UNREADABLE = (OSError, ValueError, EOFError)      # what np.load raises on a truncated / foreign file
+
+
+def cache_params(feature_type: str, cfg: Any) -> dict:
+    """The dictionary whose JSON form is hashed (and stored in the manifest)."""
+    if isinstance(cfg, Mapping):
+        return {"feature_type": feature_type, **cfg}
+    if not is_dataclass(cfg):
+        raise TypeError("cfg must be an MfccConfig-like dataclass or a dict")
+    values = {f.name: getattr(cfg, f.name) for f in fields(cfg)}
+    if not values.get("n_fft"):
+        values["n_fft"] = values["frame_length"]
+    if values.get("f_max") is None:
+        values["f_max"] = values["sample_rate"] / 2
+    return {"feature_type": feature_type, **values}
+
+
+def cache_digest(params: Mapping) -> str:
+    text = json.dumps(dict(params), sort_keys=True, ensure_ascii=True)
+    return hashlib.sha1(text.encode("utf-8")).hexdigest()[:12]
+
+
+def write_npy_atomic(path: Path, array: np.ndarray) -> None:
+    """np.save under a unique temporary name in the target directory, then rename over `path`."""
+    path.parent.mkdir(parents=True, exist_ok=True)
+    scratch = path.parent / f"{path.name}.{uuid.uuid4().hex}.tmp"
+    try:
+        with open(scratch, "wb") as handle:
+            np.save(handle, array)
+        os.replace(scratch, path)
+    except BaseException:
+        scratch.unlink(missing_ok=True)
+        raise
+
+
+def read_npy_shape(path: Path) -> tuple:
+    """Shape from the .npy header alone (the manifest needs it for files that were already cached)."""
+    with open(path, "rb") as handle:
+        major, _minor = np.lib.format.read_magic(handle)
+        reader = np.lib.format.read_array_header_1_0 if major == 1 else np.lib.format.read_array_header_2_0
+        return tuple(reader(handle)[0])
+
+
+def _record(item, path: Path, shape) -> dict:
+    return {"filename": item.filename, "fold": item.fold, "path": str(path), "shape": [int(s) for s in shape]}
 
 
 class BatchFeatureCache:
+    """Same directory layout and files as the reference's FeatureCache, filled a batch at a time."""
+
     def __init__(self, root: str | Path = "outputs/features", enabled: bool = True):
         self.root = Path(root)
         self.enabled = enabled
 
-    # ---- naming: identical to FeatureCache._cfg_dict / params_hash / feature_path --------------------
-    @staticmethod
-    def _cfg_dict(cfg: Any) -> dict:
-        params = asdict(cfg) if is_dataclass(cfg) else dict(cfg)
-        params["n_fft"] = (cfg.n_fft if not isinstance(cfg, dict) else cfg.get("n_fft")) or params["frame_length"]
-        if params.get("f_max") is None:
-            params["f_max"] = params["sample_rate"] / 2
-        return params
-
+    # ---- naming --------------------------------------------------------------------------------------
     def params_hash(self, feature_type: str, cfg: Any) -> tuple[str, dict]:
-        params = {"feature_type": feature_type, **self._cfg_dict(cfg)}
-        payload = json.dumps(params, sort_keys=True, ensure_ascii=True)
-        return hashlib.sha1(payload.encode("utf-8")).hexdigest()[:12], params
+        params = cache_params(feature_type, cfg)
+        return cache_digest(params), params
 
     def feature_dir(self, feature_type: str, cfg: Any) -> Path:
-        return self.root / feature_type / self.params_hash(feature_type, cfg)[0]
+        return self.root.joinpath(feature_type, cache_digest(cache_params(feature_type, cfg)))
 
     def feature_path(self, item, feature_type: str, cfg: Any) -> Path:
-        return self.feature_dir(feature_type, cfg) / f"fold{item.fold}" / f"{item.filename}.npy"
+        return self.feature_dir(feature_type, cfg).joinpath(f"fold{item.fold}", item.filename + ".npy")
 
-    # ---- I/O ---------------------------------------------------------------------------------------
-    @staticmethod
-    def _save_one(path: Path, feat: np.ndarray) -> None:
-        path.parent.mkdir(parents=True, exist_ok=True)
-        tmp = path.with_suffix(path.suffix + f".{uuid.uuid4().hex}.tmp")
-        with tmp.open("wb") as f:
-            np.save(f, feat)
-        os.replace(tmp, path)
-
+    # ---- I/O -----------------------------------------------------------------------------------------
     def load_feature(self, item, feature_type: str, cfg: Any) -> np.ndarray | None:
-        """Cache hit or None; a corrupt file is removed like cache.py:56-63 does."""
+        """The cached array, or None on a miss.  An unreadable file counts as a miss and is deleted,
+        so that the next writer replaces it (cache.py:56-63)."""
         if not self.enabled:
             return None
         path = self.feature_path(item, feature_type, cfg)
-        if path.exists():
-            try:
-                return np.load(path)
-            except (OSError, ValueError, EOFError):
-                try:
-                    path.unlink()
-                except OSError:
-                    pass
-        return None
+        if not path.is_file():
+            return None
+        try:
+            return np.load(path)
+        except _UNREADABLE:
+            path.unlink(missing_ok=True)
+            return None
 
     def save_features(self, items: Sequence[Any], feats: np.ndarray, feature_type: str, cfg: Any,
                       workers: int = 8) -> list[dict]:
@@ -86,36 +122,29 @@ class BatchFeatureCache:
         feats = np.asarray(feats)
         if feats.shape[0] != len(items):
             raise ValueError("one feature array per item expected")
-        paths = [self.feature_path(it, feature_type, cfg) for it in items]
-        arrays = [np.ascontiguousarray(feats[i], dtype=np.float32) for i in range(len(items))]
-        if workers > 1 and len(items) > 1:
+        base = self.feature_dir(feature_type, cfg)                      # hash once per batch, not per file
+        jobs = [(base.joinpath(f"fold{it.fold}", it.filename + ".npy"), np.ascontiguousarray(feats[i], dtype=np.float32))
+                for i, it in enumerate(items)]
+        if workers > 1 and len(jobs) > 1:
             with ThreadPoolExecutor(max_workers=workers) as pool:
-                list(pool.map(self._save_one, paths, arrays))
+                for _ in pool.map(lambda job: write_npy_atomic(*job), jobs):
+                    pass
         else:
-            for p, a in zip(paths, arrays):
-                self._save_one(p, a)
-        return [{"filename": it.filename, "fold": it.fold, "path": str(p), "shape": list(a.shape)}
-                for it, p, a in zip(items, paths, arrays)]
+            for job in jobs:
+                write_npy_atomic(*job)
+        return [_record(it, path, arr.shape) for it, (path, arr) in zip(items, jobs)]
 
     def write_manifest(self, feature_type: str, cfg: Any, records: Iterable[dict]) -> Path:
         digest, params = self.params_hash(feature_type, cfg)
-        records = list(records)
-        manifest = {
-            "feature_type": feature_type,
-            "hash": digest,
-            "params": params,
-            "created_at": datetime.now(timezone.utc).replace(tzinfo=None).isoformat() + "Z",
-            "num_files": len(records),
-            "files": records,
-        }
-        out_dir = self.feature_dir(feature_type, cfg)
-        out_dir.mkdir(parents=True, exist_ok=True)
-        path = out_dir / "manifest.json"
-        with path.open("w", encoding="utf-8") as f:
-            json.dump(manifest, f, indent=2, ensure_ascii=True)
-        return path
+        files = list(records)
+        stamp = datetime.now(timezone.utc).replace(tzinfo=None).isoformat() + "Z"
+        body = dict(zip(MANIFEST_KEYS, (feature_type, digest, params, stamp, len(files), files)))
+        target = self.root.joinpath(feature_type, digest, "manifest.json")
+        target.parent.mkdir(parents=True, exist_ok=True)
+        target.write_text(json.dumps(body, indent=2, ensure_ascii=True), encoding="utf-8")
+        return target
 
-    # ---- batched precompute (GPU) -----------------------------------------------------------------------
+    # ---- batched precompute (GPU) --------------------------------------------------------------------
     def precompute(self, items: Sequence[Any], cfg: Any, feature_types: Iterable[str] = FEATURE_TYPES,
                    clips: np.ndarray | None = None, loader: Callable[[Any], np.ndarray] | None = None,
                    batch: int = 256, workers: int = 8, normalize: bool = True, skip_existing: bool = True) -> dict:
@@ -134,11 +163,13 @@ class BatchFeatureCache:
         items = list(items)
         if clips is None and loader is None:
             raise ValueError("precompute needs clips or a loader")
+        dirs = {ft: self.feature_dir(ft, cfg) for ft in feature_types}
         records = {ft: [] for ft in feature_types}
         for s in range(0, len(items), batch):
             chunk = items[s:s + batch]
-            todo = [i for i, it in enumerate(chunk)
-                    if not (skip_existing and all(self.feature_path(it, ft, cfg).exists() for ft in feature_types))]
+            paths = {ft: [dirs[ft].joinpath(f"fold{it.fold}", it.filename + ".npy") for it in chunk] for ft in feature_types}
+            todo = [i for i in range(len(chunk))
+                    if not (skip_existing and all(paths[ft][i].is_file() for ft in feature_types))]
             if todo:
                 if clips is not None:
                     x = np.asarray(clips[s:s + batch])[todo]
@@ -148,11 +179,5 @@ class BatchFeatureCache:
                 for ft in feature_types:
                     self.save_features([chunk[i] for i in todo], out[ft], ft, cfg, workers=workers)
             for ft in feature_types:
-                for it in chunk:
-                    p = self.feature_path(it, ft, cfg)
-                    with p.open("rb") as f:
-                        ver = np.lib.format.read_magic(f)
-                        shape = (np.lib.format.read_array_header_1_0(f) if ver == (1, 0)
-                                 else np.lib.format.read_array_header_2_0(f))[0]
-                    records[ft].append({"filename": it.filename, "fold": it.fold, "path": str(p), "shape": list(shape)})
+                records[ft].extend(_record(it, p, read_npy_shape(p)) for it, p in zip(chunk, paths[ft]))
         return {ft: self.write_manifest(ft, cfg, records[ft]) for ft in feature_types}

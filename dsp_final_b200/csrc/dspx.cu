@@ -160,7 +160,9 @@ static int launch_generic(const dspx_plan *pl, const float *clips, int64_t n_cli
     const size_t smem = gen_smem_bytes(G, pl->M, gp.n_mels);
     const int64_t grid = n_clips * gp.ctas_per_clip;
     DSPX_REQUIRE(grid > 0 && grid < (int64_t)2147483647, "batch too large for one launch (%lld CTAs)", (long long)grid);
-    DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DSPX_REQUIRE(smem <= MAX_OPTIN_SMEM, "generic kernel needs %zu bytes of shared memory", smem);
+    static std::atomic<unsigned char> optin[64];
+    DSPX_CUDA_CHECK(optin_max_smem(feat_generic_kernel, optin, pl->device));
     feat_generic_kernel<<<(unsigned)grid, GEN_THREADS, smem, st>>>(gp);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
@@ -212,9 +214,10 @@ static int stft_device(const dspx_plan *pl, const float *clips, int64_t n_clips,
 static int ensure_pipe(dspx_plan *pl, size_t in_bytes, size_t out_bytes, bool stage_in, bool stage_out, HostPipe **out,
                        size_t f32_bytes = 0)
 {
-    if (!pl->host_pipe) pl->host_pipe = new (std::nothrow) HostPipe();
+    // the HostPipe object itself is created with the plan; its streams and buffers are (re)sized here, with
+    // hp->mu held by the caller for the whole pipelined call
     auto *hp = static_cast<HostPipe *>(pl->host_pipe);
-    if (!hp) { set_error("out of host memory"); return DSPX_ENOMEM; }
+    if (!hp) { set_error("plan has no host pipeline state"); return DSPX_EINVAL; }
     for (int i = 0; i < PIPE_SLOTS; i++) {
         if (!hp->stream[i]) DSPX_CUDA_CHECK(cudaStreamCreateWithFlags(&hp->stream[i], cudaStreamNonBlocking));
     }
@@ -310,6 +313,7 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     DSPX_REQUIRE(clips && n_clips >= 0 && clip_stride >= clip_len, "bad clip buffer arguments");
     if (n_clips == 0) return DSPX_OK;
     DeviceGuard guard(pl->device);
+    if (!guard.ok) { set_error("cudaSetDevice(%d) failed", pl->device); return DSPX_ECUDA; }
     const size_t clip_bytes = (size_t)clip_len * elem;
     const size_t lm_b = (mode == 0 && o_logmel) ? (size_t)T * pl->cfg.n_mels * 4 : 0;
     const bool need_mfcc = mode == 0 && (o_mfcc || o_embed);
@@ -328,11 +332,24 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     const size_t off_mf = align256(lm_b * chunk), off_em = off_mf + align256(mf_b * chunk);
     const size_t off_st = off_em + align256(em_b * chunk);
     const size_t out_bytes = off_st + align256(st_b * chunk);
-    HostPipe *hp = nullptr;
+    // One pipelined call at a time per plan: the lock covers the (re)allocation of the staging buffers as well
+    // as their use, so concurrent callers sharing a plan queue up here instead of freeing each other's slots.
+    HostPipe *hp = static_cast<HostPipe *>(pl->host_pipe);
+    DSPX_REQUIRE(hp, "plan has no host pipeline state");
+    std::lock_guard<std::mutex> lock(hp->mu);
     int rc = ensure_pipe(pl, clip_bytes * chunk, out_bytes, !in_pinned, !out_pinned, &hp,
                          elem == 2 ? (size_t)clip_len * 4 * chunk : 0);
     if (rc != DSPX_OK) return rc;
-    std::lock_guard<std::mutex> lock(hp->mu);
+    // "_host" contract: nothing may still be reading the caller's input or writing the caller's output when
+    // the call returns, also on the error paths below
+    struct Quiesce {
+        HostPipe *hp;
+        ~Quiesce()
+        {
+            for (int i = 0; i < PIPE_SLOTS; i++)
+                if (hp->stream[i]) cudaStreamSynchronize(hp->stream[i]);
+        }
+    } quiesce{hp};
 
     struct Pending { int64_t first = -1, count = 0; } pend[PIPE_SLOTS];
     auto drain = [&](int s) -> int {
@@ -436,10 +453,13 @@ int dspx_plan_create(const dspx_config *cfg, int device, dspx_plan **out)
     if (!p) { set_error("out of host memory"); return DSPX_ENOMEM; }
     p->cfg = *cfg;
     p->device = device;
+    p->host_pipe = new (std::nothrow) HostPipe();
+    if (!p->host_pipe) { set_error("out of host memory"); delete p; return DSPX_ENOMEM; }
     const int nfft_raw = cfg->n_fft > 0 ? cfg->n_fft : cfg->frame_length;
     const int64_t P = next_pow_two(nfft_raw);
     if (P < 16 || P > 8192) {
         set_error("transform length %lld unsupported (power of two in [16, 8192])", (long long)P);
+        plan_free_device(p);
         delete p;
         return DSPX_EUNSUPPORTED;
     }
@@ -461,9 +481,9 @@ int dspx_plan_create(const dspx_config *cfg, int device, dspx_plan **out)
     build_dct2(cfg->n_mfcc, cfg->n_mels, p->host.dct2);
 
     DeviceGuard guard(device);
-    if (!guard.ok) { set_error("cudaSetDevice(%d) failed", device); delete p; return DSPX_ECUDA; }
+    if (!guard.ok) { set_error("cudaSetDevice(%d) failed", device); plan_free_device(p); delete p; return DSPX_ECUDA; }
     cudaDeviceProp prop{};
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); delete p; return DSPX_ECUDA; }
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); plan_free_device(p); delete p; return DSPX_ECUDA; }
     p->sm_count = prop.multiProcessorCount;
 
     std::vector<float> w32(p->host.window.begin(), p->host.window.end());
@@ -703,6 +723,26 @@ int dspx_fft_c2c(const float *in_dev, int64_t batch, int64_t n_in, int64_t n, in
     return DSPX_OK;
 }
 
+// Tuning / test knobs of the ranking path, read from the environment once per process (never in the launch
+// path): DSPX_TOPK = tc | f32 | f64 forces a kernel, DSPX_TOPK_SPLITS fixes the database split count.
+struct TopkKnobs {
+    const char *force;
+    bool f64;
+    long long splits;
+};
+static const TopkKnobs &topk_knobs()
+{
+    static const TopkKnobs k = [] {
+        TopkKnobs t{};
+        t.force = getenv("DSPX_TOPK");
+        t.f64 = getenv("DSPX_TOPK_F64") != nullptr;
+        const char *e = getenv("DSPX_TOPK_SPLITS");
+        t.splits = e ? atoll(e) : 0;
+        return t;
+    }();
+    return k;
+}
+
 static int topk_splits(int64_t nq, int64_t ndb, int sm_count)
 {
     const int64_t qtiles = (nq + TK_QPC - 1) / TK_QPC;
@@ -759,8 +799,9 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     unsigned long long *shared_thr = reinterpret_cast<unsigned long long *>(ws);
     // Filter kernels (single-chunk dimensions, lists that fit beside the tiles), all with exact float64 re-scoring:
     // tensor-core TF32 filter, else packed-FP32 filter, else the all-float64 kernel.  DSPX_TOPK = tc | f32 | f64 forces one.
-    const char *force = getenv("DSPX_TOPK");
-    const bool want_f64 = getenv("DSPX_TOPK_F64") || (force && !strcmp(force, "f64"));
+    const TopkKnobs &knobs = topk_knobs();
+    const char *force = knobs.force;
+    const bool want_f64 = knobs.f64 || (force && !strcmp(force, "f64"));
     const bool tc_ok = dim <= 32 && k <= TC_MAX_K;
     const bool f32_ok = dim <= 32 && topk_f32_smem_bytes(dim, k, dim == 26 ? 26 : 32) <= 200 * 1024;
     const bool use_tc = !want_f64 && tc_ok && !(force && !strcmp(force, "f32") && f32_ok);
@@ -825,10 +866,7 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
             const double cost = waves / (double)c * (1.0 + 0.02 * (double)c);
             if (cost < best - 1e-12) { best = cost; sp = c; }
         }
-        if (const char *e = getenv("DSPX_TOPK_SPLITS")) {                       // tuning knob
-            const int64_t v = atoll(e);
-            if (v >= 1 && v <= TK_MAX_SPLITS) sp = v;
-        }
+        if (knobs.splits >= 1 && knobs.splits <= TK_MAX_SPLITS) sp = knobs.splits;      // tuning knob
         int64_t rows = (ndb + sp - 1) / sp;
         rows = (rows + TK_ROWS - 1) / TK_ROWS * TK_ROWS;
         tp.rows_per_split = rows;
@@ -845,10 +883,10 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
             dim3 cgrid((unsigned)qtiles, (unsigned)tp.n_splits);
             const size_t smem = topk_tc_smem_bytes(k);
             if (dim == 26) {
-                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_tc_smem_bytes(TC_MAX_K)));
+                { static std::atomic<unsigned char> optin[64]; DSPX_CUDA_CHECK(optin_max_smem(cosine_topk_tc_kernel<26>, optin, dev)); }
                 cosine_topk_tc_kernel<26><<<cgrid, TC_THREADS, smem, st>>>(cp);
             } else {
-                DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_tc_smem_bytes(TC_MAX_K)));
+                { static std::atomic<unsigned char> optin[64]; DSPX_CUDA_CHECK(optin_max_smem(cosine_topk_tc_kernel<0>, optin, dev)); }
                 cosine_topk_tc_kernel<0><<<cgrid, TC_THREADS, smem, st>>>(cp);
             }
         } else {
@@ -860,21 +898,21 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
         dim3 fgrid((unsigned)qtiles, (unsigned)tp.n_splits);
         if (dim == 26) {
             const size_t smem = topk_f32_smem_bytes(dim, k, 26);
-            DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_f32_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            { static std::atomic<unsigned char> optin[64]; DSPX_CUDA_CHECK(optin_max_smem(cosine_topk_f32_kernel<26>, optin, dev)); }
             cosine_topk_f32_kernel<26><<<fgrid, TKF_WARPS * 32, smem, st>>>(fp);
         } else {
             const size_t smem = topk_f32_smem_bytes(dim, k, 32);
-            DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            { static std::atomic<unsigned char> optin[64]; DSPX_CUDA_CHECK(optin_max_smem(cosine_topk_f32_kernel<32>, optin, dev)); }
             cosine_topk_f32_kernel<32><<<fgrid, TKF_WARPS * 32, smem, st>>>(fp);
         }
         }
     } else if (dim == 26) {                            // MFCC embeddings: 2 x 13, the whole vector in one chunk
         const size_t smem = topk_smem_bytes(dim, k, 26);
-        DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { static std::atomic<unsigned char> optin[64]; DSPX_CUDA_CHECK(optin_max_smem(cosine_topk_kernel<26>, optin, dev)); }
         cosine_topk_kernel<26><<<grid, TK_WARPS * 32, smem, st>>>(tp);
     } else {
         const size_t smem = topk_smem_bytes(dim, k, 32);
-        DSPX_CUDA_CHECK(cudaFuncSetAttribute(cosine_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { static std::atomic<unsigned char> optin[64]; DSPX_CUDA_CHECK(optin_max_smem(cosine_topk_kernel<32>, optin, dev)); }
         cosine_topk_kernel<32><<<grid, TK_WARPS * 32, smem, st>>>(tp);
     }
     DSPX_CUDA_CHECK(cudaGetLastError());

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -52,6 +53,22 @@ const char *get_error();
             return DSPX_EINVAL;                 \
         }                                       \
     } while (0)
+
+// Opt-in dynamic shared memory: a per-function, per-device attribute shared by every plan and thread.  It is
+// set once per (kernel, device) to the architectural maximum and never lowered, so launches of plans with
+// different shared-memory sizes cannot race on it (the size actually used is a launch argument).
+constexpr size_t MAX_OPTIN_SMEM = 227 * 1024;
+#if defined(__CUDACC__)
+template <class Kernel>
+inline cudaError_t optin_max_smem(Kernel kernel, std::atomic<unsigned char> (&done)[64], int device)
+{
+    std::atomic<unsigned char> &flag = done[device & 63];
+    if (flag.load(std::memory_order_acquire)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_OPTIN_SMEM);
+    if (e == cudaSuccess) flag.store(1, std::memory_order_release);
+    return e;
+}
+#endif
 
 // Tables built on the host in float64 with the reference's formulas, rounded
 // once to float32 (the mel bin floor is only safe in

@@ -948,6 +948,7 @@ struct W8PlanData {
     int ctas_per_sm;
     size_t smem;
     size_t smem_wide;        // 0 when the 20-warp configuration does not fit
+    bool share;              // hop == n_fft / 2: the two frames of a pair share rows (DSPX_W8_NOSHARE=1 at plan creation disables)
 };
 
 inline int warp8_prepare(dspx_plan *pl)
@@ -963,6 +964,7 @@ inline int warp8_prepare(dspx_plan *pl)
     pd->ctas_per_sm = (tb.r1 != 16 && smem * 2 + 2048 <= 227 * 1024) ? 2 : 1;
     const size_t wide = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_WIDE);
     pd->smem_wide = (tb.r1 != 16 && wide + 1024 <= 227 * 1024 && !getenv("DSPX_W8_NARROW")) ? wide : 0;
+    pd->share = (2 * pl->cfg.hop_length == pl->P) && !getenv("DSPX_W8_NOSHARE");
     pl->fast_host = pd;
     DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));
     DSPX_CUDA_CHECK(cudaMemcpy(pl->d_fast_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -982,12 +984,8 @@ int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_c
 template <int R1, bool PRE, bool STFT, bool SHARE, int NW>
 inline int w8_launch_nw(const W8Params &p, size_t smem, int device, int64_t ctas, cudaStream_t st)
 {
-    // the opt-in shared-memory limit is a per-function attribute shared by all plans: only ever raise it
-    static size_t smem_set[64] = {};
-    if (smem > smem_set[device & 63]) {
-        DSPX_CUDA_CHECK(cudaFuncSetAttribute(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[device & 63] = smem;
-    }
+    static std::atomic<unsigned char> optin[64];
+    DSPX_CUDA_CHECK(optin_max_smem(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW>, optin, device));
     feat_warp8_kernel<R1, PRE, STFT, SHARE, NW><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
@@ -1044,7 +1042,7 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.n_mels = pl->cfg.n_mels;
     p.n_mfcc = pl->cfg.n_mfcc;
     p.prefetch = 1;
-    p.share = (2 * pl->cfg.hop_length == pl->P) && !getenv("DSPX_W8_NOSHARE");
+    p.share = pd->share;
     p.alpha = (float)pl->cfg.pre_emphasis;
     p.win_a = pl->cfg.window == DSPX_WINDOW_HANN ? 0.25f : (pl->cfg.window == DSPX_WINDOW_HAMMING ? 0.27f : 0.5f);
     p.win_b = pl->cfg.window == DSPX_WINDOW_HANN ? -0.25f : (pl->cfg.window == DSPX_WINDOW_HAMMING ? -0.23f : 0.f);

@@ -31,9 +31,12 @@ def test_digests_and_paths_are_the_published_ones(tmp_path, known_answers):
     assert bc.params_hash("mfcc", cfg)[1] == known_answers["cache_params_mfcc_1024_512"]
     it = _items(1)[0]
     assert bc.feature_path(it, "mfcc", cfg) == tmp_path / "mfcc" / "e637fe1e8db0" / "fold1" / f"{it.filename}.npy"
+    # dict configs are hashed verbatim, no n_fft / f_max defaulting (cache.py:35-38; how retrieval_ml.py keys its
+    # embedding_* caches): digests below were produced by the reference's FeatureCache.params_hash
     assert bc.params_hash("mfcc", {"sample_rate": 44100, "frame_length": 1024, "hop_length": 512, "n_fft": None,
                                    "n_mels": 40, "n_mfcc": 13, "f_min": 0.0, "f_max": None, "pre_emphasis": 0.97,
-                                   "window": "hann"})[0] == "e637fe1e8db0"
+                                   "window": "hann"})[0] == "6f264003971b"
+    assert bc.params_hash("embedding_panns", {"model": "cnn14", "sr": 32000})[0] == "b2b4aab840f8"
 
 
 def test_save_load_manifest_roundtrip(tmp_path):
