@@ -114,6 +114,54 @@ class BatchFeatureCache:
             path.unlink(missing_ok=True)
             return None
 
+    def save_feature(self, path: Path, feat: np.ndarray) -> None:
+        """Reference-named single-file writer (cache.py:89-94)."""
+        write_npy_atomic(Path(path), np.asarray(feat))
+
+    def compute_feature(self, item, feature_type: str, cfg: Any) -> np.ndarray:
+        """One clip from item.path: load_audio + normalize_audio + the fused kernel (cache.py:65-74)."""
+        return self._compute([item], feature_type, cfg, None)[0]
+
+    def get_feature(self, item, feature_type: str, cfg: Any) -> np.ndarray:
+        """Reference-named per-item access (cache.py:76-87): cache hit, else compute and store."""
+        return self.get_features([item], feature_type, cfg)[0]
+
+    def _compute(self, items: Sequence[Any], feature_type: str, cfg: Any, loader) -> list:
+        from .batch import features_batch
+        from .retrieval import _by_length, _load_clips
+
+        if feature_type not in FEATURE_TYPES:
+            raise ValueError(f"Unsupported feature_type: {feature_type}")
+        if isinstance(cfg, Mapping):
+            raise ValueError("get_feature requires MfccConfig for mfcc/log_mel")      # cache.py:83
+        clips = _load_clips(list(items), cfg, loader)
+        feats: list = [None] * len(clips)
+        for _shape, rows in _by_length(clips).items():
+            out = features_batch(np.stack([clips[i] for i in rows], axis=0), cfg, (feature_type,))[feature_type]
+            for j, i in enumerate(rows):
+                feats[i] = out[j]
+        return feats
+
+    def get_features(self, items: Sequence[Any], feature_type: str, cfg: Any, loader=None, batch: int = 256,
+                     workers: int = 8) -> list:
+        """Batched get_feature: hits are read, misses are computed `batch` clips at a time on the GPU and
+        written in the reference's format.  Returns float32 [n_frames, n_coef] arrays in item order."""
+        items = list(items)
+        feats = [self.load_feature(it, feature_type, cfg) for it in items]
+        missing = [i for i, f in enumerate(feats) if f is None]
+        for s in range(0, len(missing), batch):
+            rows = missing[s:s + batch]
+            made = self._compute([items[i] for i in rows], feature_type, cfg, loader)
+            for i, f in zip(rows, made):
+                feats[i] = np.ascontiguousarray(f, dtype=np.float32)
+            if self.enabled:
+                base = self.feature_dir(feature_type, cfg)
+                jobs = [(base.joinpath(f"fold{items[i].fold}", items[i].filename + ".npy"), feats[i]) for i in rows]
+                with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+                    for _ in pool.map(lambda job: write_npy_atomic(*job), jobs):
+                        pass
+        return feats
+
     def save_features(self, items: Sequence[Any], feats: np.ndarray, feature_type: str, cfg: Any,
                       workers: int = 8) -> list[dict]:
         """Write feats[i] ([n_frames, n_coef]) for items[i]; returns the manifest records."""

@@ -33,26 +33,58 @@ def _mfcc_embedding(signal: np.ndarray, cfg: MfccConfig) -> np.ndarray:
     return features_batch(sig, cfg, ("embed",))["embed"][0].astype(np.float64)
 
 
-def compute_embeddings(items: List[Any], cfg: MfccConfig, feature_cache=None, loader=None) -> np.ndarray:
-    """[N, 2*n_mfcc] embeddings (src/retrieval/retrieval.py:26-43).
+def _load_clips(items: List[Any], cfg: MfccConfig, loader) -> list:
+    """One array per item: what the reference's load_audio + normalize_audio return (float32), or -- when every
+    file is mono 16-bit PCM at cfg.sample_rate, the ESC-50 case -- the raw int16 samples, which the GPU converts
+    and peak-normalises with bit-identical results (src/utils/audio.py:19-38 as used by retrieval.py:35-36)."""
+    from .audio import load_audio, load_pcm16, normalize_audio
 
-    With a feature_cache the cached float32 MFCCs are reduced on the GPU in one
-    launch (equal shapes) -- the path scripts/tasks/run_retrieval.py always takes.
-    Without one, `loader(item) -> float32 samples` stands in for the reference's
-    load_audio + normalize_audio (file decoding is out of scope, SURVEY.md 2 row 7);
-    clips of equal length go through the fused kernel as one batch.
+    if loader is not None:
+        return [np.asarray(loader(item), dtype=np.float32).reshape(-1) for item in items]
+    pcm = [load_pcm16(item.path, cfg.sample_rate) for item in items]
+    if all(p is not None for p in pcm):
+        return pcm
+    clips = []
+    for item in items:
+        audio, _ = load_audio(item.path, target_sr=cfg.sample_rate)
+        clips.append(normalize_audio(audio).astype(np.float32))
+    return clips
+
+
+def _by_length(arrays: list) -> dict:
+    groups: dict = {}
+    for i, a in enumerate(arrays):
+        groups.setdefault(a.shape, []).append(i)
+    return groups
+
+
+def compute_embeddings(items: List[Any], cfg: MfccConfig, feature_cache=None, loader=None) -> np.ndarray:
+    """[N, 2*n_mfcc] embeddings, concat(mean_t, std_t) of each clip's MFCCs (src/retrieval/retrieval.py:26-43).
+
+    Reference signature (items, cfg, feature_cache=None); `loader(item) -> samples` optionally replaces the
+    audio decoding.  Without a cache the clips are read from item.path (load_audio + normalize_audio
+    semantics) and clips of equal length go through the fused kernel as one batch.  With a cache the
+    float32 MFCCs come from it (any object with the reference's get_feature; BatchFeatureCache fills its
+    misses in GPU batches) and are reduced on the GPU -- the path scripts/tasks/run_retrieval.py takes.
     """
+    items = list(items)
+    if not items:
+        return np.zeros((0, 2 * cfg.n_mfcc), np.float32)
     if feature_cache is not None:
-        feats = [np.asarray(feature_cache.get_feature(item, "mfcc", cfg), dtype=np.float32) for item in items]
-        if feats and all(f.shape == feats[0].shape for f in feats):
-            return embed_stats(np.stack(feats, axis=0))
-        return np.stack([embed_stats(f[None])[0] for f in feats], axis=0)
-    if loader is None:
-        raise ValueError("compute_embeddings needs a feature_cache or a loader(item) -> samples callable")
-    clips = [np.asarray(loader(item), dtype=np.float32).reshape(-1) for item in items]
-    if clips and all(c.shape == clips[0].shape for c in clips):
-        return features_batch(np.stack(clips, axis=0), cfg, ("embed",))["embed"]
-    return np.stack([features_batch(c[None, :], cfg, ("embed",))["embed"][0] for c in clips], axis=0)
+        if hasattr(feature_cache, "get_features"):
+            feats = feature_cache.get_features(items, "mfcc", cfg, loader=loader)
+        else:
+            feats = [feature_cache.get_feature(item, "mfcc", cfg) for item in items]
+        feats = [np.asarray(f, dtype=np.float32) for f in feats]
+        out = np.empty((len(items), 2 * feats[0].shape[1]), np.float32)
+        for shape, rows in _by_length(feats).items():
+            out[rows] = embed_stats(np.stack([feats[i] for i in rows], axis=0))
+        return out
+    clips = _load_clips(items, cfg, loader)
+    out = np.empty((len(items), 2 * cfg.n_mfcc), np.float32)
+    for shape, rows in _by_length(clips).items():
+        out[rows] = features_batch(np.stack([clips[i] for i in rows], axis=0), cfg, ("embed",))["embed"]
+    return out
 
 
 def _dev_matrix(x):
