@@ -79,6 +79,63 @@ def measured_tensor_peak() -> tuple[float, str]:
     return 2250.0, "fallback"
 
 
+def workload_config(outputs: str, clips: int, world: int) -> dict:
+    """`config` of the JSON line: the workload, identical for our arm and for the CPU (reference) arm."""
+    return {"workload": f"ESC-50-shaped synthetic set: {clips} clips x 5 s @44.1 kHz per GPU, frame {FL} hop {HOP}, "
+                        f"{N_MELS} mels, {N_MFCC} MFCC (BASELINE.json configs[1])",
+            "outputs": outputs, "clips_per_gpu": clips,
+            "l2_policy": "inputs_larger_than_l2 (1.76 GB per pass vs 126 MB L2)", "parallelism": f"clip-sharded x{world}"}
+
+
+def gpu_topology(index: int) -> dict:
+    """PCI bus id, NUMA node and local CPU list of GPU `index` (sysfs; -1 / None when the kernel does not say)."""
+    info = {"gpu": index, "pci": None, "numa_node": -1, "local_cpus": None}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        info["pci"] = bus
+        dev = Path("/sys/bus/pci/devices") / bus.lower()[-12:]
+        if (dev / "numa_node").exists():
+            info["numa_node"] = int((dev / "numa_node").read_text().strip())
+        if (dev / "local_cpulist").exists():
+            info["local_cpus"] = (dev / "local_cpulist").read_text().strip()
+    except Exception:
+        pass
+    return info
+
+
+def parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in (text or "").split(","):
+        part = part.strip()
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(index: int) -> dict:
+    """Pin this rank's threads to the CPUs local to its GPU *before* pinned buffers are allocated, so that
+    first-touch places the staging memory on the GPU's NUMA node.  No-op when the platform reports one node."""
+    topo = gpu_topology(index)
+    try:
+        allowed = os.sched_getaffinity(0)
+        local = parse_cpulist(topo["local_cpus"]) & allowed
+        if topo["numa_node"] >= 0 and local and local != allowed:
+            os.sched_setaffinity(0, local)
+            topo["bound"] = True
+        else:
+            topo["bound"] = False
+        topo["affinity_cpus"] = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        topo["bound"] = False
+    return topo
+
+
 def host_cores() -> int:
     """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS instead)."""
     try:
@@ -147,7 +204,7 @@ def cpu_arm(args, n_frames: int):
     cfg = O.OracleConfig(SR, FL, HOP, n_mels=N_MELS, n_mfcc=N_MFCC)
     cores = host_cores()
     want = tuple(n for n in ("mfcc", "log_mel") if n in args.outputs)
-    per_step = max(4 * cores, 16)
+    per_step = max(4 * cores, 64)                          # bounded sample of the 2000-clip set: >= 4 clips per core
     clips = synth.host_clips(min(per_step, 64), seed=1234)
     if clips.shape[0] < per_step:
         clips = np.concatenate([clips] * ((per_step + clips.shape[0] - 1) // clips.shape[0]))[:per_step]
@@ -167,10 +224,8 @@ def run_reference(args) -> None:
     # keep the whole run within a few minutes whatever K is
     budget = 150.0
     steps, warm = args.steps, max(0, args.warmup - 1)
-    if one * (steps + warm) > budget:
-        shrink = max(1, int(per_step * budget / (one * (steps + warm))))
-        clips = clips[:shrink]
-        per_step = clips.shape[0]
+    if one * (steps + warm) > budget:                       # never below 4 clips per core: cut steps instead
+        steps = max(1, int(budget / one) - warm)
     for _ in range(warm):
         O.features_batch(clips, cfg, want=want, n_threads=cores)
     t0 = time.perf_counter()
@@ -178,14 +233,14 @@ def run_reference(args) -> None:
         O.features_batch(clips, cfg, want=want, n_threads=cores)
     dt = time.perf_counter() - t0
     value = per_step * CLIP_SECONDS * steps / dt
-    sample = f"{per_step} synthetic 5 s clips per step x {steps} steps, C port of src/dsp (complex128 radix-2), OpenMP over clips"
+    sample = (f"{per_step} of the {args.clips} synthetic 5 s clips per step x {steps} steps, C port of src/dsp "
+              f"(complex128 radix-2), OpenMP over clips on {cores} host threads")
     line = {
         "impl": "reference", "metric": "mfcc_logmel_audio_seconds_per_second", "value": value,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"ESC-50-shaped synthetic set, frame {FL} hop {HOP}, {args.outputs} (bounded sample)",
-                   "outputs": args.outputs},
+        "config": workload_config(args.outputs, args.clips, args.gpus),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -208,6 +263,7 @@ def run_ours(args) -> None:
     rank, world, local = init_process_group()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    topo = bind_to_gpu_numa(local)          # before any pinned allocation (first touch decides the NUMA node)
     cfg = MfccConfig(sample_rate=SR, frame_length=FL, hop_length=HOP, n_mels=N_MELS, n_mfcc=N_MFCC)
     plan = get_plan(cfg, local, args.kernel)
     n_frames = plan.num_frames(CLIP_LEN)
@@ -338,13 +394,48 @@ def run_ours(args) -> None:
         del r_q, r_db, r_idx
 
     # end to end through the host-buffer C ABI: pinned host clips in, host features out
-    e2e = None
+    e2e = e2e_pcm16 = None
     if args.e2e_steps > 0:
         h_clips = torch.empty((b, CLIP_LEN), dtype=torch.float32, pin_memory=True)
         h_clips.copy_(clips)
         h_mf = torch.empty((b, n_frames, N_MFCC), dtype=torch.float32, pin_memory=True) if mf is not None else None
         h_lm = torch.empty((b, n_frames, N_MELS), dtype=torch.float32, pin_memory=True) if lm is not None else None
         torch.cuda.synchronize(dev)
+        d2h = (h_mf.numel() * 4 if h_mf is not None else 0) + (h_lm.numel() * 4 if h_lm is not None else 0)
+
+        def timed_all_ranks(fn, reps):
+            """Wall time of `reps` calls of a synchronous host-API call, all ranks at once, max over ranks."""
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        # the ceiling of this box for the same bytes: plain pinned->device and device->pinned copies on two
+        # streams (full duplex), every rank at once -- no kernel, no library.  e2e is reported against it.
+        d_in = torch.empty((b, CLIP_LEN), dtype=torch.float32, device=dev)
+        d_out = torch.empty(d2h // 4, dtype=torch.float32, device=dev)
+        h_out = torch.empty(d2h // 4, dtype=torch.float32, pin_memory=True)
+        s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def copy_step():
+            with torch.cuda.stream(s_up):
+                d_in.copy_(h_clips, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_out.copy_(d_out, non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+
+        dt_copy = timed_all_ranks(copy_step, args.e2e_steps)
+        ceiling = world * b * CLIP_SECONDS * args.e2e_steps / dt_copy
+        copy_gbs = (b * CLIP_LEN * 4 + d2h) * args.e2e_steps / dt_copy / 1e9
+        del d_in, d_out, h_out
 
         def e2e_step():
             _lib.check(lib.dspx_features_host(plan.handle, h_clips.data_ptr(), b, CLIP_LEN, CLIP_LEN,
@@ -352,26 +443,18 @@ def run_ours(args) -> None:
                                               h_mf.data_ptr() if h_mf is not None else None, None),
                        "dspx_features_host")
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        d2h = (h_mf.numel() * 4 if h_mf is not None else 0) + (h_lm.numel() * 4 if h_lm is not None else 0)
+        dt = timed_all_ranks(e2e_step, args.e2e_steps)
         e2e = {"value": world * b * CLIP_SECONDS * args.e2e_steps / dt, "unit": "audio-s/s",
                "h2d_bytes_per_step": b * CLIP_LEN * 4, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-               "api": "dspx_features_host (pinned host buffers in and out)"}
+               "api": "dspx_features_host (pinned host buffers in and out)",
+               "copy_ceiling": {"value": ceiling, "unit": "audio-s/s", "gb_per_s_per_gpu": copy_gbs,
+                                "what": "same bytes as plain cudaMemcpyAsync pinned<->device, both directions overlapped, all ranks at once"},
+               "frac_of_copy_ceiling": (world * b * CLIP_SECONDS * args.e2e_steps / dt) / ceiling}
         # the host path and the device path run the same kernel: results must be identical
         if h_mf is not None:
             assert torch.equal(h_mf[:8], mf[:8].cpu()), "host-pipeline result differs from device-path result"
-        # informational: the same call fed with PCM16 clips (what ESC-50 files hold) --
-        # int16 -> float32 and peak normalisation run on the GPU, host->device bytes halve
+        # the same call fed with PCM16 clips (what ESC-50 files hold): int16 -> float32 and peak
+        # normalisation happen in the feature kernel's sample loads, host->device bytes halve
         h_pcm = torch.empty((b, CLIP_LEN), dtype=torch.int16, pin_memory=True)
         h_pcm.copy_((clips * 32767.0).round().to(torch.int16))
         torch.cuda.synchronize(dev)
@@ -382,19 +465,69 @@ def run_ours(args) -> None:
                                                     h_mf.data_ptr() if h_mf is not None else None, None),
                        "dspx_features_host_pcm16")
 
-        pcm_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            pcm_step()
-        torch.cuda.synchronize(dev)
-        dtp = time.perf_counter() - t0
-        ttp = torch.tensor([dtp], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ttp, op=dist.ReduceOp.MAX)
-        e2e["pcm16_variant"] = {"value": world * b * CLIP_SECONDS * args.e2e_steps / float(ttp.item()), "unit": "audio-s/s",
-                                "h2d_bytes_per_step": b * CLIP_LEN * 2, "api": "dspx_features_host_pcm16"}
+        dtp = timed_all_ranks(pcm_step, args.e2e_steps)
+        e2e_pcm16 = {"value": world * b * CLIP_SECONDS * args.e2e_steps / dtp, "unit": "audio-s/s",
+                     "h2d_bytes_per_step": b * CLIP_LEN * 2, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                     "api": "dspx_features_host_pcm16 (int16 PCM in, peak normalisation on the GPU)"}
+        pcm_mf_sel = h_mf[:2].clone() if h_mf is not None else None
+        pcm_src_sel = h_pcm[:2].clone()
+        del h_clips, h_pcm
 
+    # configs[4] in miniature, N > 1 only: every rank holds 125 000 clip embeddings (100 000 database + 25 000
+    # queries, the 80/20 split); ONE NCCL all-gather of the database shards, local top-20, one all-reduce of the
+    # hit counters (dsp_final_b200.dist.sharded_retrieval = src/tasks/retrieval.py:11-21 at scale)
+    sharded_info = None
+    sharded_check = None
+    if world > 1 and args.retrieval_steps > 0:
+        from dsp_final_b200 import dist as D
+        from dsp_final_b200.batch import features_batch as fb
+
+        S_DB, S_Q = 100_000, 25_000
+        real = fb(clips, cfg, ("embed",))["embed"]                      # 2000 real MFCC embeddings of this rank's clips
+        real_t = torch.arange(rank * b, rank * b + b, device=dev, dtype=torch.int32) % 50
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(4000 + rank)
+        src = torch.randint(0, b, (S_DB + S_Q,), generator=gen, device=dev)
+        emb = real[src] * (1.0 + 0.05 * torch.randn((S_DB + S_Q, real.shape[1]), generator=gen, device=dev))
+        tgt = real_t[src].contiguous()
+        db_e, db_t, q_e, q_t = emb[:S_DB].contiguous(), tgt[:S_DB].contiguous(), emb[S_DB:].contiguous(), tgt[S_DB:].contiguous()
+        D.sharded_retrieval(db_e, db_t, q_e, q_t, (10, 20))             # warm-up (NCCL channels, workspaces)
+        barrier()
+        phases = []
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.retrieval_steps):
+            prof = {}
+            s_res, s_idx = D.sharded_retrieval(db_e, db_t, q_e, q_t, (10, 20), profile=prof)
+            phases.append(prof)
+        s1.record(stream)
+        barrier()
+        s_ms = s0.elapsed_time(s1) / args.retrieval_steps
+        tt = torch.tensor([s_ms] + [float(np.mean([p[k] for p in phases])) for k in ("gather_ms", "topk_ms", "reduce_ms")],
+                          dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        s_ms, g_ms, t_ms, r_ms2 = [float(v) for v in tt.tolist()]
+        gbytes = phases[-1]["gather_bytes"]
+        sharded_info = {"value": world * S_Q / (s_ms * 1e-3), "unit": "queries/s", "ms_per_step": s_ms,
+                        "n_queries": world * S_Q, "n_db": world * S_DB, "dim": int(emb.shape[1]), "k": 20,
+                        "pair_scores_per_s": world * S_Q * world * S_DB / (s_ms * 1e-3),
+                        "all_gather_ms": g_ms, "all_gather_bytes_received_per_rank": gbytes,
+                        "all_gather_gb_per_s_per_rank": gbytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else None,
+                        "topk_ms": t_ms, "hits_all_reduce_ms": r_ms2, "steps": args.retrieval_steps,
+                        "top10_top20": [[k, h / n] for k, h, n in s_res],
+                        "what": "per-rank shards of clustered MFCC embeddings (real embeddings of this rank's clips, jittered 5 %); "
+                                "NCCL all-gather of database rows + targets, dspx_cosine_topk on the local queries, all-reduce of hit counts"}
+        if rank == 0:
+            full_db = D.all_gather_rows(db_e).cpu().numpy()
+            sharded_check = (q_e[:64].cpu().numpy(), full_db, s_idx[:64].cpu().numpy())
+        else:
+            D.all_gather_rows(db_e)
+        del emb, db_e, q_e
+
+    topos = [topo]
+    if world > 1:
+        topos = [None] * world
+        dist.all_gather_object(topos, topo)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -419,6 +552,14 @@ def run_ours(args) -> None:
     if retrieval_info is not None:
         parity["retrieval_top20_identical"] = bool(np.array_equal(r_sel_idx, O.cosine_topk(r_sel_q, r_db_host, 20)))
         parity["retrieval_queries_checked"] = 8
+    if sharded_check is not None:
+        sq, sdb, sidx = sharded_check
+        parity["sharded_top20_identical"] = bool(np.array_equal(sidx, O.cosine_topk(sq, sdb, 20)))
+        parity["sharded_queries_checked"] = int(sq.shape[0])
+    if e2e_pcm16 is not None and pcm_mf_sel is not None:
+        x = pcm_src_sel.numpy().astype(np.float32) / np.float32(32768.0)
+        x = x / np.max(np.abs(x), axis=1, keepdims=True)
+        parity["pcm16_mfcc_rel_err"] = O.relative_error(pcm_mf_sel.numpy(), O.features_batch(x, ocfg, want=("mfcc",))["mfcc"])
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
@@ -439,12 +580,10 @@ def run_ours(args) -> None:
         "metric": "mfcc_logmel_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ESC-50-shaped synthetic set: {b} clips x 5 s @44.1 kHz per GPU, frame {FL} hop {HOP}, "
-                               f"{N_MELS} mels, {N_MFCC} MFCC (BASELINE.json configs[1])",
-                   "outputs": args.outputs, "clips_per_gpu": b, "kernel": plan.kernel,
-                   "l2_policy": "inputs_larger_than_l2 (1.76 GB per pass vs 126 MB L2)", "parallelism": f"clip-sharded x{world}"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps, "stft": stft_info, "retrieval": retrieval_info,
-        "clocks": clocks, "parity": parity,
+        "config": workload_config(args.outputs, b, world),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_pcm16": e2e_pcm16, "gpu_launches": args.steps,
+        "stft": stft_info, "retrieval": retrieval_info, "retrieval_sharded": sharded_info,
+        "clocks": clocks, "parity": parity, "topology": topos,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -95,13 +95,16 @@ def all_reduce_sum_ints(values: Sequence[int], device=None) -> list[int]:
 
 
 def sharded_retrieval(local_db_emb, local_db_targets, local_q_emb, local_q_targets, k_list: Iterable[int],
-                      topk_fn=None, hits_fn=None):
+                      topk_fn=None, hits_fn=None, profile: dict | None = None):
     """Distributed evaluate_retrieval (src/retrieval/retrieval.py:52-72 at scale).
 
     Each rank holds a shard of database embeddings/targets and a shard of queries.
     Returns ([(k, hits_global, n_queries_global)], local_topk_idx).  topk_fn/hits_fn
     default to the GPU kernels; the gloo CPU tests inject reference callables so the
-    exchange logic is tested without a GPU.
+    exchange logic is tested without a GPU.  With `profile` (a dict) and CUDA tensors,
+    the device time of the three phases is recorded with CUDA events on the current
+    stream: profile["gather_ms" | "topk_ms" | "reduce_ms"], plus "gather_bytes" (what
+    this rank receives) and "db_rows".
     """
     import torch
 
@@ -111,11 +114,32 @@ def sharded_retrieval(local_db_emb, local_db_targets, local_q_emb, local_q_targe
         topk_fn = topk_fn or R.cosine_topk
         hits_fn = hits_fn or R.hits_at_k
     k_list = [int(k) for k in k_list]
+    on_gpu = isinstance(local_q_emb, torch.Tensor) and local_q_emb.is_cuda
+    marks = []
+
+    def mark():
+        if profile is not None and on_gpu:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(local_q_emb.device))
+            marks.append(ev)
+
+    mark()
     db = all_gather_rows(local_db_emb)
     tdb = all_gather_rows(local_db_targets.reshape(-1, 1)).reshape(-1)
+    mark()
     kmax = min(max(k_list), db.shape[0])
     idx = topk_fn(local_q_emb, db, kmax)
+    mark()
     hits = [hits_fn(idx, min(k, kmax), tdb, local_q_targets) for k in k_list]
     dev = local_q_emb.device if isinstance(local_q_emb, torch.Tensor) else None
     tot = all_reduce_sum_ints(hits + [int(local_q_emb.shape[0])], device=dev)
+    mark()
+    if profile is not None:
+        profile["db_rows"] = int(db.shape[0])
+        profile["gather_bytes"] = int((db.shape[0] - local_db_emb.shape[0]) * (db.shape[1] * db.element_size() + tdb.element_size()))
+        if len(marks) == 4:
+            marks[-1].synchronize()
+            profile["gather_ms"] = marks[0].elapsed_time(marks[1])
+            profile["topk_ms"] = marks[1].elapsed_time(marks[2])
+            profile["reduce_ms"] = marks[2].elapsed_time(marks[3])
     return [(k, tot[i], tot[-1]) for i, k in enumerate(k_list)], idx
