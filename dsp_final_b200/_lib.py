@@ -74,6 +74,7 @@ _SIGNATURES = {
     "dspx_features": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP]),
     "dspx_log_mel_nchw": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "dspx_embed_stats": (_I32, [_VP, _I64, _I64, _I32, _VP, _VP]),
+    "dspx_cmvn": (_I32, [_VP, _I64, _I64, _I32, C.c_double, _VP]),
     "dspx_features_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP]),
     "dspx_pcm16_to_float": (_I32, [_VP, _I64, _I64, _I64, _I32, _VP, _I64, _VP]),
     "dspx_features_host_pcm16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP, _VP, _VP]),

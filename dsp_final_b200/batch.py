@@ -244,6 +244,29 @@ def embed_stats(feats):
     return out.cpu().numpy() if to_host else out
 
 
+def cmvn(feats, eps: float = 1e-10):
+    """Cepstral mean / variance normalisation per clip: (x - mean_t) / (std_t + eps) over [B, T, C] features.
+
+    Not part of the reference pipeline (src/dsp/mfcc.py:102-109 end at log and DCT); offered because
+    BASELINE.json's north_star names a log/CMVN epilogue.  torch CUDA tensors are normalised in place
+    and returned; NumPy input returns a new array.
+    """
+    import torch
+
+    _lib.require_device()
+    host = not _is_cuda_tensor(feats)
+    f = torch.as_tensor(np.ascontiguousarray(np.asarray(feats, dtype=np.float32))).cuda() if host else feats
+    if f.dtype != torch.float32 or not f.is_contiguous():
+        raise ValueError("cmvn needs a contiguous float32 tensor")
+    v = f if f.dim() == 3 else f[None]
+    b, t, c = v.shape
+    dev = f.device.index
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().dspx_cmvn(v.data_ptr(), b, t, c, float(eps), torch.cuda.current_stream(dev).cuda_stream),
+                   "dspx_cmvn")
+    return f.cpu().numpy() if host else f
+
+
 def fft_batch(x, n: int | None = None, inverse: bool = False):
     """Batched complex FFT over the last axis with the reference's length rule (fft.py:27-42).
 

@@ -633,6 +633,20 @@ int dspx_embed_stats(const float *feats_dev, int64_t n_clips, int64_t n_frames, 
     return launch_embed(feats_dev, n_clips, n_frames, n_coef, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int dspx_cmvn(float *feats_dev, int64_t n_clips, int64_t n_frames, int n_coef, double eps, void *stream)
+{
+    DSPX_REQUIRE(feats_dev, "null argument");
+    DSPX_REQUIRE(n_clips >= 0 && n_frames > 0 && n_coef > 0 && eps >= 0.0, "bad shape");
+    DSPX_REQUIRE(n_clips < (int64_t)2147483647, "too many clips for one launch");
+    if (n_clips == 0) return DSPX_OK;
+    const int cw = n_coef < 128 ? n_coef : 128;
+    const size_t smem = ((size_t)(128 / cw) * n_coef + 2 * (size_t)n_coef) * sizeof(double);
+    DSPX_REQUIRE(smem <= 48 * 1024, "n_coef %d too large for cmvn", n_coef);
+    cmvn_kernel<<<(unsigned)n_clips, 128, smem, static_cast<cudaStream_t>(stream)>>>(feats_dev, n_frames, n_coef, eps);
+    DSPX_CUDA_CHECK(cudaGetLastError());
+    return DSPX_OK;
+}
+
 int dspx_features_host(const dspx_plan *plan, const float *clips_host, int64_t n_clips, int64_t clip_len,
                        int64_t clip_stride, float *logmel_out_host, float *mfcc_out_host, float *embed_out_host)
 {

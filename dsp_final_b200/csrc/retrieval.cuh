@@ -67,6 +67,52 @@ __global__ void __launch_bounds__(128) embed_stats_kernel(const float *feats, in
     }
 }
 
+// ---- CMVN: cepstral mean / variance normalisation over the frames of each clip ----------------------
+// BASELINE.json north_star names "a log/CMVN epilogue"; the reference has none (src/dsp/mfcc.py:102-109 stop
+// at log and DCT), so it is an option that defaults to off.  y[t,c] = (x[t,c] - mean_t x[.,c]) / (std_t x[.,c] + eps),
+// population std, statistics in float64 exactly like embed_stats_kernel (same summation order), in place.
+// One CTA per clip: two passes for the statistics, a third applies them (22 KB per clip: L2-resident).
+__global__ void __launch_bounds__(128) cmvn_kernel(float *feats, int64_t n_frames, int n_coef, double eps)
+{
+    extern __shared__ double es_sm[];                  // [groups][n_coef] partials, [n_coef] means, [n_coef] 1/(std+eps)
+    const int64_t clip = blockIdx.x;
+    float *f = feats + (size_t)clip * n_frames * n_coef;
+    const int cw = n_coef < 128 ? n_coef : 128;
+    const int groups = 128 / cw;
+    const int tid = threadIdx.x;
+    const int ty = tid / cw, tx = tid - ty * cw;
+    double *mean = es_sm + (size_t)groups * n_coef;
+    double *rstd = mean + n_coef;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int c0 = 0; c0 < n_coef; c0 += cw) {
+            const int c = c0 + tx;
+            double acc = 0.0;
+            if (ty < groups && c < n_coef) {
+                const double mu = pass ? mean[c] : 0.0;
+                for (int64_t t = ty; t < n_frames; t += groups) {
+                    const double v = (double)f[(size_t)t * n_coef + c] - mu;
+                    acc += pass ? v * v : v;
+                }
+                es_sm[(size_t)ty * n_coef + c] = acc;
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < n_coef; c += 128) {
+            double s = 0.0;
+            for (int g = 0; g < groups; g++) s += es_sm[(size_t)g * n_coef + c];
+            s /= (double)n_frames;
+            if (pass == 0) mean[c] = s;
+            else rstd[c] = 1.0 / (sqrt(s) + eps);
+        }
+        __syncthreads();
+    }
+    const int64_t total = n_frames * n_coef;
+    for (int64_t i = tid; i < total; i += 128) {
+        const int c = (int)(i % n_coef);
+        f[i] = (float)(((double)f[i] - mean[c]) * rstd[c]);
+    }
+}
+
 // ---- row normalisation to float64 ---------------------------------------------
 template <typename T>
 __global__ void normalize_rows_kernel(const T *x, int64_t n, int dim, double *out)

@@ -130,6 +130,11 @@ int dspx_dct2(const float *x_dev, int64_t rows, int n, int n_mfcc, float *out_de
 int dspx_embed_stats(const float *feats_dev, int64_t n_clips, int64_t n_frames, int n_coef,
                      float *out_dev, void *stream);
 
+/* Optional CMVN epilogue (BASELINE.json north_star "a log/CMVN epilogue"; the reference applies none after
+ * mfcc.py:102-109, so callers opt in): in place over [n_clips, n_frames, n_coef] f32 features,
+ * y = (x - mean_t) / (std_t + eps) per clip and coefficient, population std, statistics in float64. */
+int dspx_cmvn(float *feats_dev, int64_t n_clips, int64_t n_frames, int n_coef, double eps, void *stream);
+
 /* Host-buffer twins of the two calls above (what FeatureCache.compute_feature,
  * src/features/cache.py:65-74, and a batched precompute need): pinned staging,
  * chunked H2D / kernel / D2H overlap inside; synchronous. */

@@ -391,6 +391,29 @@ int orc_embedding(const double *feats, int64_t T, int C, double *out)
 }
 
 /*
+ * ---- CMVN option (no reference counterpart: src/dsp/mfcc.py:102-109 end at log and DCT) ----
+ * BASELINE.json's north_star names a log/CMVN epilogue; this is the CPU statement of the option the
+ * GPU side offers (dspx_cmvn): y = (x - mean_t) / (std_t + eps), population std, float64, in place.
+ */
+int orc_cmvn(double *feats, int64_t T, int C, double eps)
+{
+    if (T <= 0 || C <= 0) return ORC_EINVAL;
+    for (int c = 0; c < C; c++) {
+        double s = 0.0;
+        for (int64_t t = 0; t < T; t++) s += feats[t * C + c];
+        const double mean = s / (double)T;
+        double v = 0.0;
+        for (int64_t t = 0; t < T; t++) {
+            const double d = feats[t * C + c] - mean;
+            v += d * d;
+        }
+        const double r = 1.0 / (sqrt(v / (double)T) + eps);
+        for (int64_t t = 0; t < T; t++) feats[t * C + c] = (feats[t * C + c] - mean) * r;
+    }
+    return ORC_OK;
+}
+
+/*
  * Batched front end used for the CPU baseline and for large parity sets:
  * clips float32 [B, len] -> mfcc float32 [B,T,n_mfcc] (the cache dtype,
  * src/features/cache.py:74) and/or log-mel float32 [B,T,n_mels] and/or

@@ -205,6 +205,13 @@ def embedding(feats) -> np.ndarray:
     return out
 
 
+def cmvn(feats, eps: float = 1e-10) -> np.ndarray:
+    """(x - mean_t) / (std_t + eps) per coefficient of one clip's [T, C] features, float64 (option, see orc_cmvn)."""
+    f = np.array(feats, dtype=np.float64, order="C", copy=True)
+    _check(lib().orc_cmvn(_p(f, C.c_double), C.c_int64(f.shape[0]), f.shape[1], C.c_double(eps)), "cmvn")
+    return f
+
+
 def features_batch(clips, cfg, want=("mfcc", "log_mel", "embed"), n_threads: int = 0):
     """float32 [B, L] -> dict of float32 arrays; all host threads by default."""
     x = np.ascontiguousarray(np.asarray(clips, dtype=np.float32))

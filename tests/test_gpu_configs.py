@@ -236,3 +236,90 @@ def test_sharded_retrieval_nccl(torch_cuda):
     for p in procs:
         p.join(timeout=60)
     assert sorted(out) == [(0, "ok"), (1, "ok")], out
+
+
+def test_cmvn_option_matches_oracle(torch_cuda):
+    """north_star's "log/CMVN epilogue": off by default (the reference has none), bit-for-bit float64 statistics."""
+    torch = torch_cuda
+    from dsp_final_b200 import synth
+    from dsp_final_b200.batch import cmvn, features_batch
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+    from oracle import oracle as O
+
+    cfg = MfccConfig(sample_rate=44100, frame_length=1024, hop_length=512)
+    clips = torch.as_tensor(synth.host_clips(6, seed=3, length=66_150)).cuda()
+    out = features_batch(clips, cfg, ("mfcc", "log_mel"))
+    for name in ("mfcc", "log_mel"):
+        plain = out[name].cpu().numpy()
+        normed = cmvn(out[name].clone()).cpu().numpy()
+        for b in range(plain.shape[0]):
+            want = O.cmvn(plain[b])
+            assert np.max(np.abs(normed[b] - want)) <= 1e-6 * max(1.0, np.max(np.abs(want))), (name, b)
+            assert np.allclose(normed[b].mean(axis=0), 0.0, atol=1e-5) and np.allclose(normed[b].std(axis=0), 1.0, atol=1e-4)
+    host = cmvn(out["mfcc"].cpu().numpy())                           # NumPy in -> new NumPy array out
+    assert np.array_equal(host, cmvn(out["mfcc"].clone()).cpu().numpy())
+    const = torch.ones((2, 10, 3), device="cuda")
+    assert torch.equal(cmvn(const.clone()), torch.zeros_like(const))   # zero variance: (x - mean) / (0 + eps) = 0
+
+
+def test_logmel_batches_feed_the_epoch_loop(torch_cuda):
+    """Row f3: LogMelBatches yields what DataLoader(Esc50FeatureDataset(..., postprocess=to_tensor)) yields
+    (train_cnn.py:46-55; per item torch.tensor(log_mel.T, float32).unsqueeze(0), transforms.py:16-18)."""
+    torch = torch_cuda
+    from dsp_final_b200 import synth
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+    from dsp_final_b200.stream import LogMelBatches
+    from oracle import oracle as O
+
+    n, length = 37, 44_100
+    cfg = MfccConfig(sample_rate=44100, frame_length=1024, hop_length=512, n_mels=128)
+    host = synth.host_clips(n, seed=12, length=length)
+    targets = synth.labels(n)
+    ref = O.features_batch(host, O.OracleConfig(44100, 1024, 512, n_mels=128), want=("log_mel",))["log_mel"]
+    want = torch.tensor(np.transpose(ref, (0, 2, 1)), dtype=torch.float32).unsqueeze(1)       # [N, 1, n_mels, T]
+
+    def collect(loader):
+        xs, ys = [], []
+        for feats, y in loader:
+            assert feats.is_cuda and feats.dtype == torch.float32 and y.dtype == torch.int64 and feats.shape[1:] == (1, 128, 85)
+            xs.append(feats.cpu())
+            ys.append(y.cpu())
+        return torch.cat(xs), torch.cat(ys)
+
+    for clips in (torch.as_tensor(host).cuda(), host):                 # resident in HBM / streamed from the host
+        loader = LogMelBatches(clips, targets, cfg, batch_size=8)
+        assert len(loader) == 5 and len(loader.dataset) == n
+        x, y = collect(loader)
+        assert x.shape == (n, 1, 128, 85) and torch.equal(y, torch.as_tensor(targets, dtype=torch.int64))
+        assert rel_err(x.numpy(), want.numpy()) < TOL
+        assert len(LogMelBatches(clips, targets, cfg, batch_size=8, drop_last=True)) == 4
+        sh = LogMelBatches(clips, targets, cfg, batch_size=8, shuffle=True, seed=4)
+        x1, y1 = collect(sh)
+        x2, y2 = collect(sh)                                           # next epoch: another permutation of the same set
+        assert not torch.equal(y1, y2) or n < 3
+        for xa, ya in ((x1, y1), (x2, y2)):
+            assert sorted(ya.tolist()) == sorted(targets.tolist())
+            # every shuffled row is one of the unshuffled rows, with its own target
+            key = {xr.numpy().tobytes(): int(t) for xr, t in zip(x, y)}
+            assert all(key[xr.numpy().tobytes()] == int(t) for xr, t in zip(xa, ya))
+    # PCM16 clips: converted and peak-normalised on the GPU
+    pcm = np.round(host * 32767.0).astype(np.int16)
+    xp, _ = collect(LogMelBatches(pcm, targets, cfg, batch_size=16))
+    f = pcm.astype(np.float32) / np.float32(32768.0)
+    f = f / np.max(np.abs(f), axis=1, keepdims=True)
+    refp = O.features_batch(f, O.OracleConfig(44100, 1024, 512, n_mels=128), want=("log_mel",))["log_mel"]
+    assert rel_err(xp[:, 0].numpy(), np.transpose(refp, (0, 2, 1))) < TOL
+    # and it drives the reference's epoch loop shape (classification.py:18-33): a tiny model, one optimizer step per batch
+    model = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3, padding=1), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
+                                torch.nn.Linear(4, 50)).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    loader = LogMelBatches(torch.as_tensor(host).cuda(), targets, cfg, batch_size=8, shuffle=True)
+    seen = 0
+    for feats, y in loader:
+        feats, y = feats.to("cuda"), y.to("cuda")
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(feats), y)
+        loss.backward()
+        opt.step()
+        seen += y.size(0)
+    assert seen == len(loader.dataset) and bool(torch.isfinite(loss))
