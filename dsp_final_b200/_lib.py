@@ -72,6 +72,8 @@ _SIGNATURES = {
     "dspx_plan_read_table": (_I32, [_VP, _I32, _VP, _I64]),
     "dspx_stft": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP, _VP]),
     "dspx_features": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP]),
+    "dspx_embeddings_workspace": (_SZ, [_VP, _I64]),
+    "dspx_embeddings": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _SZ, _VP]),
     "dspx_log_mel_nchw": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "dspx_embed_stats": (_I32, [_VP, _I64, _I64, _I32, _VP, _VP]),
     "dspx_cmvn": (_I32, [_VP, _I64, _I64, _I32, C.c_double, _VP]),

@@ -96,17 +96,27 @@ def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int
         plan = get_plan(cfg, dev, kernel)
         b, length = x.shape
         t = plan.num_frames(length)
-        need_mfcc = "mfcc" in want or "embed" in want
+        # embeddings without MFCCs: accumulated inside the feature kernel (no [B, T, n_mfcc] tensor at all)
+        fused = ("embed" in want and "mfcc" not in want and plan.kernel == "warp8"
+                 and x.data_ptr() % 8 == 0 and x.stride(0) % 2 == 0)
+        need_mfcc = "mfcc" in want or ("embed" in want and not fused)
         with torch.cuda.device(dev):
             out = {}
             lm = torch.empty((b, t, plan.n_mels), dtype=torch.float32, device=x.device) if "log_mel" in want else None
             mf = torch.empty((b, t, plan.n_mfcc), dtype=torch.float32, device=x.device) if need_mfcc else None
             em = torch.empty((b, 2 * plan.n_mfcc), dtype=torch.float32, device=x.device) if "embed" in want else None
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(lib.dspx_features(plan.handle, x.data_ptr(), b, length, x.stride(0),
-                                         lm.data_ptr() if lm is not None else None,
-                                         mf.data_ptr() if mf is not None else None,
-                                         em.data_ptr() if em is not None else None, stream), "dspx_features")
+            if fused:
+                ws_bytes = int(lib.dspx_embeddings_workspace(plan.handle, b))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+                _lib.check(lib.dspx_embeddings(plan.handle, x.data_ptr(), b, length, x.stride(0), em.data_ptr(),
+                                               lm.data_ptr() if lm is not None else None, ws.data_ptr(), ws_bytes, stream),
+                           "dspx_embeddings")
+            else:
+                _lib.check(lib.dspx_features(plan.handle, x.data_ptr(), b, length, x.stride(0),
+                                             lm.data_ptr() if lm is not None else None,
+                                             mf.data_ptr() if mf is not None else None,
+                                             em.data_ptr() if em is not None else None, stream), "dspx_features")
         if lm is not None:
             out["log_mel"] = lm
         if "mfcc" in want:

@@ -186,12 +186,29 @@ static int launch_embed(const float *feats, int64_t n_clips, int64_t T, int C, f
     return DSPX_OK;
 }
 
+// embed without mfcc: the fused path -- the kernel accumulates per-clip sums into `eacc` ([n_clips][2][n_mfcc]
+// int64, caller-provided scratch) and embed_finalize_kernel writes mean / std; no MFCC tensor exists anywhere.
 static int features_device(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
-                           int64_t clip_stride, float *logmel, float *mfcc, float *embed, cudaStream_t st, int nchw = 0)
+                           int64_t clip_stride, float *logmel, float *mfcc, float *embed, cudaStream_t st, int nchw = 0,
+                           long long *eacc = nullptr)
 {
     const int64_t T = dspx_num_frames(pl, clip_len);
     if (T < 0) return DSPX_EINVAL;
     int rc;
+    if (embed && !mfcc) {
+        if (!eacc || pl->kernel != DSPX_KERNEL_WARP8 || !warp8_can_launch(clips, n_clips, clip_stride, T)) {
+            set_error("embeddings without an MFCC buffer need the warp8 kernel and 8-byte aligned clips with an even stride");
+            return DSPX_EUNSUPPORTED;
+        }
+        const int C = pl->cfg.n_mfcc;
+        DSPX_CUDA_CHECK(cudaMemsetAsync(eacc, 0, (size_t)n_clips * 2 * C * sizeof(long long), st));
+        rc = launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, logmel, nullptr, st, nchw, nullptr, 0, eacc);
+        if (rc != DSPX_OK) return rc;
+        const int64_t total = n_clips * C;
+        embed_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(eacc, n_clips, T, C, embed);
+        DSPX_CUDA_CHECK(cudaGetLastError());
+        return DSPX_OK;
+    }
     if (pl->kernel == DSPX_KERNEL_WARP8)
         rc = launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
     else
@@ -316,8 +333,11 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     if (!guard.ok) { set_error("cudaSetDevice(%d) failed", pl->device); return DSPX_ECUDA; }
     const size_t clip_bytes = (size_t)clip_len * elem;
     const size_t lm_b = (mode == 0 && o_logmel) ? (size_t)T * pl->cfg.n_mels * 4 : 0;
-    const bool need_mfcc = mode == 0 && (o_mfcc || o_embed);
-    const size_t mf_b = need_mfcc ? (size_t)T * pl->cfg.n_mfcc * 4 : 0;
+    // embeddings alone: accumulated inside the feature kernel (16 bytes of scratch per coefficient instead of an
+    // MFCC tensor); otherwise they are the statistics of the MFCCs that are written anyway
+    const bool fused_embed = mode == 0 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8;
+    const bool need_mfcc = mode == 0 && (o_mfcc || (o_embed && !fused_embed));
+    const size_t mf_b = need_mfcc ? (size_t)T * pl->cfg.n_mfcc * 4 : (fused_embed ? (size_t)pl->cfg.n_mfcc * 16 : 0);
     const size_t em_b = (mode == 0 && o_embed) ? (size_t)2 * pl->cfg.n_mfcc * 4 : 0;
     const size_t st_b = mode == 1 ? (size_t)T * pl->n_bins * 8 : 0;
     const size_t out_per_clip = lm_b + mf_b + em_b + st_b;
@@ -395,7 +415,9 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
         float *d_em = em_b ? reinterpret_cast<float *>(d_o + off_em) : nullptr;
         float *d_st = st_b ? reinterpret_cast<float *>(d_o + off_st) : nullptr;
         if (mode == 0)
-            rc = features_device(pl, d_clips, cnt, clip_len, clip_len, d_lm, d_mf, d_em, st);
+            rc = fused_embed ? features_device(pl, d_clips, cnt, clip_len, clip_len, d_lm, nullptr, d_em, st, 0,
+                                               reinterpret_cast<long long *>(d_mf))
+                             : features_device(pl, d_clips, cnt, clip_len, clip_len, d_lm, d_mf, d_em, st);
         else
             rc = stft_device(pl, d_clips, cnt, clip_len, clip_len, T, pre, reinterpret_cast<float2 *>(d_st), st);
         if (rc != DSPX_OK) return rc;
@@ -611,6 +633,27 @@ int dspx_features(const dspx_plan *plan, const float *clips_dev, int64_t n_clips
     DeviceGuard guard(plan->device);
     return features_device(plan, clips_dev, n_clips, clip_len, clip_stride, logmel_out_dev, mfcc_out_dev, embed_out_dev,
                            static_cast<cudaStream_t>(stream));
+}
+
+size_t dspx_embeddings_workspace(const dspx_plan *plan, int64_t n_clips)
+{
+    if (!plan || n_clips < 0) return 0;
+    return (size_t)n_clips * 2 * plan->cfg.n_mfcc * sizeof(long long) + 256;
+}
+
+int dspx_embeddings(const dspx_plan *plan, const float *clips_dev, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                    float *embed_out_dev, float *logmel_out_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    DSPX_REQUIRE(plan && clips_dev && embed_out_dev && workspace_dev, "null argument");
+    DSPX_REQUIRE(n_clips >= 0 && clip_stride >= clip_len, "bad clip buffer arguments");
+    DSPX_REQUIRE(workspace_bytes >= dspx_embeddings_workspace(plan, n_clips), "workspace too small");
+    if (dspx_num_frames(plan, clip_len) < 0) return DSPX_EINVAL;
+    if (n_clips == 0) return DSPX_OK;
+    DeviceGuard guard(plan->device);
+    char *ws = static_cast<char *>(workspace_dev);
+    ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
+    return features_device(plan, clips_dev, n_clips, clip_len, clip_stride, logmel_out_dev, nullptr, embed_out_dev,
+                           static_cast<cudaStream_t>(stream), 0, reinterpret_cast<long long *>(ws));
 }
 
 int dspx_log_mel_nchw(const dspx_plan *plan, const float *clips_dev, int64_t n_clips, int64_t clip_len,

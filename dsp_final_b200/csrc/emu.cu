@@ -190,6 +190,8 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     c.n_mfcc = p.n_mfcc;
     c.rounds = tb.rounds;
     c.cw_lanes = tb.cw_lanes;
+    c.dct_row = tb.dct_row;
+    c.lm_part = tb.lm_part;
     const int r1 = tb.r1;
     const int units = r1 >= 8 ? r1 / 8 : 1;
     std::vector<W8Power> pw(32 * 2);
@@ -233,10 +235,15 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
             }
         for (int lane = 0; lane < 32; lane++) w8_mel_chunks(c, lane);
         for (int lane = 0; lane < 32; lane++) w8_logmel(c, lane);
-        if (c.mfccA) {
+        if (c.mfccA || c.eacc) {
             for (int c0 = 0; c0 < c.n_mfcc; c0 += c.cw_lanes) {
-                for (int lane = 0; lane < 32; lane++) w8_dct_partial(c, lane, c0);
-                for (int lane = 0; lane < 32; lane++) w8_dct_store(c, lane, c0);
+                float2 acc[32];
+                for (int lane = 0; lane < 32; lane++) acc[lane] = w8_dct_partial(c, lane, c0);
+                for (int lane = 0; lane < 32; lane++) {
+                    float2 t = acc[lane];
+                    if (c.cw_lanes == 16) { t.x += acc[lane ^ 16].x; t.y += acc[lane ^ 16].y; }    // the device's shuffle
+                    w8_dct_store(c, lane, c0, t);
+                }
             }
         }
     }

@@ -183,7 +183,10 @@ struct W8Tables {            // offsets (in floats) into the packed table blob /
     int win, tw1, tw2, ptw, ppos, cw, cflag, fdesc, dct, total;
     int rounds, n_slots;     // mel chunks: 32 lanes x rounds (rounds odd)
     int n_segs;              // run pieces emitted by the mel chunks
+    int seg_slots;           // float2 slots of the area that holds their sums (filter ranges start at even slots)
     int cw_lanes;            // DCT: coefficient lanes per part (16 or 32)
+    int dct_row;             // DCT: floats per (part, coefficient) table row (multiple of 4, odd number of 16-byte units)
+    int lm_part;             // log-mel row: float2 slots per part (filters f = part, part + parts, ... ; multiple of 2)
     int tile_floats;         // per-warp exchange / power tile
     int r1;                  // first-pass radix (4, 8, 16)
 };
@@ -200,6 +203,7 @@ struct W8Params {
     float *logmel, *mfcc;    // either may be null
     int64_t lm_ts, lm_fs;    // log-mel strides between frames / filters ([B,T,M]: M,1; [B,1,M,T]: 1,T)
     float2 *stft;            // STFT mode: complex spectrum [n_clips, n_frames, M + 1]
+    long long *eacc;         // embedding accumulators [n_clips][2][n_mfcc] (fixed point, see w8_embed_accumulate) or null
 };
 
 struct W8Ctx {               // everything one warp needs for one frame pair
@@ -215,10 +219,11 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     int firstA, firstB;      // frame starts at sample 0 of its clip (no predecessor for pre-emphasis)
     float alpha;
     float win_a, win_b;      // 0.5 w[n] = win_a + win_b cos(2 pi n / P): hann (0.25, -0.25), hamming (0.27, -0.23), rect (0.5, 0)
-    int n_mels, n_mfcc, rounds, cw_lanes, validB;
+    int n_mels, n_mfcc, rounds, cw_lanes, dct_row, lm_part, validB;
     float *logmelA, *logmelB, *mfccA, *mfccB;   // rows of the two frames (null when not requested)
     int64_t lm_fs;
     float2 *stftA, *stftB;   // STFT mode: rows of the two frames
+    long long *eacc;         // this clip's embedding accumulators: sum x [n_mfcc], sum x^2 [n_mfcc]
 };
 
 struct W8Power {             // |X|^2 of the bins one pass-3 unit owns, carried across the syncwarp
@@ -248,8 +253,8 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
     c.xbuf = reinterpret_cast<float4 *>(warp_smem);
     c.pbuf = reinterpret_cast<float2 *>(warp_smem);
     c.seg = c.pbuf + (W8_CSTRIDE * tb.n_slots + 16);          // 2 n_segs sums in filter order + one dump slot
-    c.lm = c.seg + 2 * tb.n_segs + 2;
-    c.dsc = c.lm + n_mels;
+    c.lm = c.seg + tb.seg_slots;                             // seg_slots is even: 16-byte aligned for the DCT's 128-bit loads
+    c.dsc = c.lm + (32 / tb.cw_lanes) * tb.lm_part;
 }
 
 // ---- window and first-pass twiddles without table loads (R1 <= 8) ---------------------------------------
@@ -325,15 +330,25 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
             const float *ph = c.validB ? pa : pa - 128 * SH;             // no frame B: rows >= R1 replay frame A's rows
             float2 x[NR];
             float pv[NR];
+#if defined(DSPX_ABL) && DSPX_ABL == 7        // timing only: no global sample loads at all
+#pragma unroll
+            for (int r = 0; r < NR; r++) { x[r] = make_float2(0.001f * (r + lane), 0.002f * (r - lane)); pv[r] = 0.003f * r; }
+#else
 #pragma unroll
             for (int r = 0; r < NR; r++) x[r] = *reinterpret_cast<const float2 *>((r >= R1 ? ph : pa) + 128 * r);
             if (PRE) {
+#if defined(DSPX_ABL) && DSPX_ABL == 6        // timing only: no predecessor loads
+#pragma unroll
+                for (int r = 0; r < NR; r++) pv[r] = x[r].y;
+#else
                 const bool edge = c.firstA && tid == 0;
                 pv[0] = *(edge ? pa : pa - 1);
                 if (edge) pv[0] = 0.f;
 #pragma unroll
                 for (int r = 1; r < NR; r++) pv[r] = (r >= R1 ? ph : pa)[128 * r - 1];
+#endif
             }
+#endif
             float y0[NR], y1[NR];
 #pragma unroll
             for (int r = 0; r < NR; r++) {
@@ -601,30 +616,65 @@ DSPX_HD void w8_store_power(const W8Ctx &c, int lane, int w, const W8Power &pw)
 // the half of a 128-byte line and the lane reads its four 16-byte pieces rotated by (lane >> 1) & 3:
 // the 128-bit loads of 8 neighbouring lanes hit 8 different bank groups (rounds is odd, so parity
 // alternates with the lane).  The weight rows (80 B apart) are stored pre-rotated to match.
+struct W8MelIn {                 // one chunk's operands: four 16-byte pieces of power values and of weights, and its flag word
+    float4 p[4], w[4];
+    int flag;
+};
+
+DSPX_HD void w8_mel_load(const W8Ctx &c, int lane, int r, W8MelIn &in)
+{
+    const int ch = lane * c.rounds + r;
+    in.flag = c.cflag[ch];                                              // bit0 first, bit1 last, 8..19 / 20..31 slots of the sums
+    const float4 *pp = reinterpret_cast<const float4 *>(c.pbuf + ch * W8_CSTRIDE);
+    const float4 *ww = reinterpret_cast<const float4 *>(c.cw + ch * W8_WROW);
+    const int rot = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        in.p[q] = pp[(q + rot) & 3];                                    // (P0A P0B P1A P1B)
+        in.w[q] = ww[q];                                                // (a0 b0 a1 b1)
+    }
+}
+
+DSPX_HD void w8_mel_accumulate(const W8Ctx &c, const W8MelIn &in, float2 &sa, float2 &sb)
+{
+    // four independent chains (even / odd bins, a / b weights): short dependency depth
+    float2 ca0 = make_float2(0.f, 0.f), cb0 = ca0, ca1 = ca0, cb1 = ca0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 p = in.p[q], w = in.w[q];
+        ca0 = fma2(make_float2(p.x, p.y), bc2(w.x), ca0);
+        cb0 = fma2(make_float2(p.x, p.y), bc2(w.y), cb0);
+        ca1 = fma2(make_float2(p.z, p.w), bc2(w.z), ca1);
+        cb1 = fma2(make_float2(p.z, p.w), bc2(w.w), cb1);
+    }
+    const float2 ca = add2(ca0, ca1), cb = add2(cb0, cb1);
+    if (in.flag & 1) { sa = ca; sb = cb; }
+    else { sa = add2(sa, ca); sb = add2(sb, cb); }
+    if (in.flag & 2) {
+        c.seg[(in.flag >> 8) & 0xfff] = sa;
+        c.seg[(unsigned)in.flag >> 20] = sb;
+    }
+}
+
 DSPX_HD void w8_mel_chunks(const W8Ctx &c, int lane)
 {
     float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#if defined(DSPX_MEL_PIPE)
+    if (c.rounds == 3) {                                                // 40 mels at n_fft 512 / 1024: all loads of the next
+        W8MelIn a, b;                                                   // round are in flight while this one is summed
+        w8_mel_load(c, lane, 0, a);
+        w8_mel_load(c, lane, 1, b);
+        w8_mel_accumulate(c, a, sa, sb);
+        w8_mel_load(c, lane, 2, a);
+        w8_mel_accumulate(c, b, sa, sb);
+        w8_mel_accumulate(c, a, sa, sb);
+        return;
+    }
+#endif
     for (int r = 0; r < c.rounds; r++) {
-        const int ch = lane * c.rounds + r;
-        const int flag = c.cflag[ch];                                   // bit0 first, bit1 last, 8..19 / 20..31 slots of the sums
-        const float4 *pp = reinterpret_cast<const float4 *>(c.pbuf + ch * W8_CSTRIDE);
-        const float4 *ww = reinterpret_cast<const float4 *>(c.cw + ch * W8_WROW);
-        float2 ca = make_float2(0.f, 0.f), cb = make_float2(0.f, 0.f);
-        const int rot = (lane >> 1) & 3;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float4 p = pp[(q + rot) & 3], w = ww[q];              // (P0A P0B P1A P1B), (a0 b0 a1 b1)
-            ca = fma2(make_float2(p.x, p.y), bc2(w.x), ca);
-            cb = fma2(make_float2(p.x, p.y), bc2(w.y), cb);
-            ca = fma2(make_float2(p.z, p.w), bc2(w.z), ca);
-            cb = fma2(make_float2(p.z, p.w), bc2(w.w), cb);
-        }
-        if (flag & 1) { sa = ca; sb = cb; }
-        else { sa = add2(sa, ca); sb = add2(sb, cb); }
-        if (flag & 2) {
-            c.seg[(flag >> 8) & 0xfff] = sa;
-            c.seg[(unsigned)flag >> 20] = sb;
-        }
+        W8MelIn in;
+        w8_mel_load(c, lane, r, in);
+        w8_mel_accumulate(c, in, sa, sb);
     }
 }
 
@@ -638,63 +688,136 @@ DSPX_HD float w8_log(float x)
 #endif
 }
 
+// Sum of one filter's run pieces: they sit in consecutive slots starting at an even (16-byte aligned) slot, so three
+// 128-bit loads fetch up to six of them and the count only predicates the adds (slots past the count hold other
+// filters' sums or stale tile data and are never added).  Filters with more pieces finish in a loop.
+DSPX_HD float2 w8_filter_sum(const W8Ctx &c, int2 d)
+{
+    const float4 *sp = reinterpret_cast<const float4 *>(c.seg + d.x);
+    const float4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0;
+    if (d.y > 0) s0 = make_float2(v0.x, v0.y);
+    if (d.y > 1) s1 = make_float2(v0.z, v0.w);
+    if (d.y > 2) s0 = add2(s0, make_float2(v1.x, v1.y));
+    if (d.y > 3) s1 = add2(s1, make_float2(v1.z, v1.w));
+    if (d.y > 4) s0 = add2(s0, make_float2(v2.x, v2.y));
+    if (d.y > 5) s1 = add2(s1, make_float2(v2.z, v2.w));
+    for (int i = 6; i < d.y; i++) s0 = add2(s0, c.seg[d.x + i]);
+    return add2(s0, s1);
+}
+
+// The row kept for the DCT is stored part-major -- slot (f % parts) * lm_part + f / parts with parts = 32 / cw_lanes --
+// so that a DCT lane finds the filters it sums in consecutive slots; slots past n_mels are zeroed (the table is
+// zero there too, but the tile still holds FFT data).  Two filters per lane are in flight at a time.
+DSPX_HD void w8_logmel_one(const W8Ctx &c, int f, int psh, float2 s)
+{
+    const int slot = ((f & psh) ? c.lm_part : 0) + (f >> psh);
+    if (f >= c.n_mels) {                                                // padding of the part rows
+        c.lm[slot] = make_float2(0.f, 0.f);
+        return;
+    }
+    const float2 v = make_float2(w8_log(fmaxf(s.x, 1e-10f)), w8_log(fmaxf(s.y, 1e-10f)));
+    c.lm[slot] = v;
+    if (c.logmelA) {
+        c.logmelA[f * c.lm_fs] = v.x;
+        if (c.validB) c.logmelB[f * c.lm_fs] = v.y;
+    }
+}
+
 DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
 {
-    for (int f = lane; f < c.n_mels; f += 32) {
-        const int4 d = c.fdesc[f];                                     // {first, count}: the sums of a filter are contiguous
-        const float2 *sp = c.seg + d.x;
-        float2 s = make_float2(0.f, 0.f);
-        for (int i = 0; i < d.y; i++) s = add2(s, sp[i]);
-        const float2 v = make_float2(w8_log(fmaxf(s.x, 1e-10f)), w8_log(fmaxf(s.y, 1e-10f)));
-        c.lm[f] = v;
-        if (c.logmelA) {
-            c.logmelA[f * c.lm_fs] = v.x;
-            if (c.validB) c.logmelB[f * c.lm_fs] = v.y;
-        }
+    const int psh = c.cw_lanes == 16 ? 1 : 0;                           // log2(parts)
+    const int n_slots = c.lm_part << psh;
+    const int2 *fd = reinterpret_cast<const int2 *>(c.fdesc);           // {first slot, count} at stride 2
+    for (int f0 = lane; f0 < n_slots; f0 += 64) {
+        const int f1 = f0 + 32;
+        const int2 d0 = fd[2 * (f0 < c.n_mels ? f0 : 0)], d1 = fd[2 * (f1 < c.n_mels ? f1 : 0)];
+        const float2 s0 = w8_filter_sum(c, d0), s1 = w8_filter_sum(c, d1);
+        w8_logmel_one(c, f0, psh, s0);
+        if (f1 < n_slots) w8_logmel_one(c, f1, psh, s1);
     }
 }
 
-// ---- phase G/H: DCT-II (table carries the factor 2) in cw_lanes-wide coefficient blocks ---------------
-// lane = part * cw_lanes + q: part p sums filters p, p + parts, ...; table row f is cw_lanes wide,
-// so a warp load touches one row per part: conflict-free.  Parts are combined through dsc[].
-DSPX_HD void w8_dct_partial(const W8Ctx &c, int lane, int c0)
+// ---- phase G: DCT-II (table carries the factor 2) ------------------------------------------------------
+// lane = part * cw_lanes + q: coefficient c0 + q, summed over the filters of `part` (f = part, part + parts, ...).
+// The lane's table row and the part's log-mel row are both contiguous, so one 128-bit table load and two
+// 128-bit (broadcast) log-mel loads feed four packed FMAs.  Table rows are an odd number of 16-byte units
+// apart: the eight lanes of a quarter warp hit eight different bank groups.
+DSPX_HD float2 w8_dct_partial(const W8Ctx &c, int lane, int c0)
 {
-    // cw_lanes is 16 or 32: shifts instead of divisions, pointer steps instead of index products, four loads per trip
     const int sh = c.cw_lanes == 16 ? 4 : 5;
-    const int parts = 32 >> sh;                                             // 2 or 1; parts * cw_lanes == 32
     const int q = lane & (c.cw_lanes - 1), part = lane >> sh;
-    const float *col = c.dct + (size_t)c0 * c.n_mels + q + (part << sh);    // block-major table, row `part`
-    const float2 *lm = c.lm + part;
-    const int n = (c.n_mels - part + parts - 1) >> (5 - sh);               // rows part, part + parts, ...
+    const int blk = c0 >> sh;                                               // c0 is a multiple of cw_lanes
+    const float4 *col = reinterpret_cast<const float4 *>(c.dct + (size_t)(blk * 32 + part * c.cw_lanes + q) * c.dct_row);
+    const float4 *lm = reinterpret_cast<const float4 *>(c.lm + part * c.lm_part);
     float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-    int i = 0;
-    for (; i + 4 <= n; i += 4) {
-        acc0 = fma2(lm[0], bc2(col[0]), acc0);
-        acc1 = fma2(lm[parts], bc2(col[32]), acc1);
-        acc0 = fma2(lm[2 * parts], bc2(col[64]), acc0);
-        acc1 = fma2(lm[3 * parts], bc2(col[96]), acc1);
-        lm += 4 * parts;
-        col += 128;
+    const int n4 = c.lm_part >> 2;                                          // whole groups of four filters
+#pragma unroll 5
+    for (int i = 0; i < n4; i++) {
+        const float4 w = col[i], a = lm[2 * i], b = lm[2 * i + 1];          // a = lm[4i], lm[4i+1]; b = lm[4i+2], lm[4i+3]
+        acc0 = fma2(make_float2(a.x, a.y), bc2(w.x), acc0);
+        acc1 = fma2(make_float2(a.z, a.w), bc2(w.y), acc1);
+        acc0 = fma2(make_float2(b.x, b.y), bc2(w.z), acc0);
+        acc1 = fma2(make_float2(b.z, b.w), bc2(w.w), acc1);
     }
-    for (; i < n; i++) {
-        acc0 = fma2(lm[0], bc2(col[0]), acc0);
-        lm += parts;
-        col += 32;
+    if (c.lm_part & 2) {                                                    // lm_part is even: at most one pair left
+        const float4 a = lm[2 * n4];
+        const float2 w = *reinterpret_cast<const float2 *>(&col[n4]);
+        acc0 = fma2(make_float2(a.x, a.y), bc2(w.x), acc0);
+        acc1 = fma2(make_float2(a.z, a.w), bc2(w.y), acc1);
     }
-    c.dsc[lane] = add2(acc0, acc1);
+    return add2(acc0, acc1);
 }
 
-DSPX_HD void w8_dct_store(const W8Ctx &c, int lane, int c0)
+// Clip embeddings (src/retrieval/retrieval.py:19-23: mean and population std of every coefficient over the frames)
+// without an MFCC round trip through HBM: every frame adds x and x^2 to per-clip accumulators.  The sums are kept
+// in 64-bit FIXED POINT (x * 2^32, x^2 * 2^20) so that the atomic adds commute exactly -- the result does not
+// depend on the order in which warps finish -- and embed_finalize_kernel turns them into mean / std in float64.
+// Range: |x| < 2^15 over 2^15 frames; resolution 2^-33 per x, 2^-21 per x^2 (std error < 1e-6 for std > 0.01).
+constexpr double W8_EFIX1 = 4294967296.0, W8_EFIX2 = 1048576.0;
+
+DSPX_HD void w8_embed_accumulate(const W8Ctx &c, int q, float2 total)
 {
-    const int cwl = c.cw_lanes;
+    const double a = (double)total.x, b = c.validB ? (double)total.y : 0.0;
+    const long long s1 = (long long)llrint(a * W8_EFIX1) + (long long)llrint(b * W8_EFIX1);
+    const long long s2 = (long long)llrint(a * a * W8_EFIX2) + (long long)llrint(b * b * W8_EFIX2);
+#if defined(__CUDA_ARCH__)
+    atomicAdd(reinterpret_cast<unsigned long long *>(c.eacc + q), (unsigned long long)s1);
+    atomicAdd(reinterpret_cast<unsigned long long *>(c.eacc + c.n_mfcc + q), (unsigned long long)s2);
+#else
+    c.eacc[q] += s1;
+    c.eacc[c.n_mfcc + q] += s2;
+#endif
+}
+
+// total = the lane's sum plus its partner's (lane ^ 16) when two parts share a coefficient
+DSPX_HD void w8_dct_store(const W8Ctx &c, int lane, int c0, float2 total)
+{
     const int q = c0 + lane;
-    if (lane < cwl && q < c.n_mfcc) {
-        float2 v = c.dsc[lane];
-        if (cwl == 16) v = add2(v, c.dsc[lane + 16]);
-        c.mfccA[q] = v.x;
-        if (c.validB) c.mfccB[q] = v.y;
+    if (lane < c.cw_lanes && q < c.n_mfcc) {
+        if (c.mfccA) {
+            c.mfccA[q] = total.x;
+            if (c.validB) c.mfccB[q] = total.y;
+        }
+        if (c.eacc) w8_embed_accumulate(c, q, total);
     }
 }
+
+#if defined(__CUDACC__)
+__global__ void embed_finalize_kernel(const long long *eacc, int64_t n_clips, int64_t n_frames, int n_coef, float *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_clips * n_coef) return;
+    const int64_t clip = i / n_coef;
+    const int q = (int)(i - clip * n_coef);
+    const long long *e = eacc + clip * 2 * n_coef;
+    const double mean = (double)e[q] / W8_EFIX1 / (double)n_frames;
+    const double ex2 = (double)e[n_coef + q] / W8_EFIX2 / (double)n_frames;
+    const double var = ex2 - mean * mean;
+    out[clip * 2 * n_coef + q] = (float)mean;
+    out[clip * 2 * n_coef + n_coef + q] = (float)sqrt(var > 0.0 ? var : 0.0);
+}
+#endif
 
 // set the per-item fields of the context (item = clip * pairs_per_clip + pair)
 DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
@@ -716,6 +839,7 @@ DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
     const int64_t n_bins = 64 * p.tb.r1 + 1;
     c.stftA = p.stft ? p.stft + rowA * n_bins : nullptr;
     c.stftB = c.stftA ? c.stftA + n_bins : nullptr;
+    c.eacc = p.eacc ? p.eacc + (int64_t)clip * 2 * p.n_mfcc : nullptr;
 }
 
 // the whole per-item sequence; SYNC is __syncwarp() on the device and a no-op in the lane-loop replay
@@ -757,14 +881,18 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     c.n_mfcc = p.n_mfcc;
     c.rounds = p.tb.rounds;
     c.cw_lanes = p.tb.cw_lanes;
+    c.dct_row = p.tb.dct_row;
+    c.lm_part = p.tb.lm_part;
     const uint32_t n_warps = gridDim.x * NW;
     for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
         w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8)>(c, lane);
         if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
+#if !defined(DSPX_ABL) || DSPX_ABL != 5
         w8_pass2<R1>(c, lane);
         __syncwarp();
+#endif
         if (STFT) {
 #pragma unroll
             for (int w = 0; w < G::UNITS; w++) w8_pass3_stft<R1>(c, lane, w);
@@ -772,23 +900,51 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
             continue;
         }
         W8Power pw[G::UNITS];
+#if defined(DSPX_ABL) && DSPX_ABL == 5
+#pragma unroll
+        for (int w = 0; w < G::UNITS; w++)
+#pragma unroll
+            for (int m = 0; m < 9; m++) pw[w].lo[m] = pw[w].hi[m] = make_float2(1.f + lane, 2.f + m);
+#else
 #pragma unroll
         for (int w = 0; w < G::UNITS; w++) w8_pass3<R1>(c, lane, w, pw[w]);
+#endif
         __syncwarp();                       // every lane has read its inputs: the tile may become P[]
+#if defined(DSPX_ABL) && DSPX_ABL == 4      // timing only: FFT passes alone (keep the power values alive)
+        {
+            float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < 9; m++) s = add2(s, add2(pw[0].lo[m], pw[0].hi[m]));
+            if (s.x == 123.456f && c.mfccA) c.mfccA[0] = s.y;
+            continue;
+        }
+#endif
 #pragma unroll
         for (int w = 0; w < G::UNITS; w++) w8_store_power<R1>(c, lane, w, pw[w]);
         __syncwarp();
+#if defined(DSPX_ABL) && DSPX_ABL == 3
+        continue;
+#endif
         w8_mel_chunks(c, lane);
         __syncwarp();
+#if defined(DSPX_ABL) && DSPX_ABL == 2
+        continue;
+#endif
         w8_logmel(c, lane);
         __syncwarp();
-        if (c.mfccA) {
+#if defined(DSPX_ABL) && DSPX_ABL == 1
+        continue;
+#endif
+        if (c.mfccA || c.eacc) {
             for (int c0 = 0; c0 < c.n_mfcc; c0 += c.cw_lanes) {
-                w8_dct_partial(c, lane, c0);
-                __syncwarp();
-                w8_dct_store(c, lane, c0);
-                __syncwarp();
+                float2 acc = w8_dct_partial(c, lane, c0);
+                if (c.cw_lanes == 16) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+                }
+                w8_dct_store(c, lane, c0, acc);
             }
+            __syncwarp();                   // the log-mel row is rewritten by the next item
         }
     }
 }
@@ -831,6 +987,10 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     tb.n_slots = 32 * rounds;
     tb.cw_lanes = n_mfcc <= 16 ? 16 : 32;
     const int dct_blocks = (n_mfcc + tb.cw_lanes - 1) / tb.cw_lanes;
+    const int parts = 32 / tb.cw_lanes;
+    tb.lm_part = (((n_mels + parts - 1) / parts) + 1) & ~1;             // filters per part, rounded up to a pair
+    tb.dct_row = (tb.lm_part + 3) & ~3;
+    if (((tb.dct_row / 4) & 1) == 0) tb.dct_row += 4;                    // odd number of 16-byte units per row
     auto al4 = [](int x) { return (x + 3) & ~3; };
     int off = 0;
     tb.win = off; off += 2 * R1 * 32 * 2;
@@ -841,7 +1001,7 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     tb.cw = off; off += tb.n_slots * W8_WROW;
     tb.cflag = off; off += tb.n_slots;
     tb.fdesc = off; off += n_mels * 4;
-    tb.dct = off; off += al4(dct_blocks * n_mels * tb.cw_lanes);
+    tb.dct = off; off += dct_blocks * 32 * tb.dct_row;
     tb.total = al4(off);
     blob.assign(tb.total, 0.f);
     const double two_pi = 2.0 * M_PI;
@@ -895,25 +1055,33 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         if (last) { seg_cnt[ch.run]++; seg++; }
     }
     tb.n_segs = std::max(seg, 1);
-    // slots of the sums: filter g reads [b sums of run g-1][a sums of run g] as one contiguous range
+    // slots of the sums: filter g reads [b sums of run g-1][a sums of run g] as one contiguous range that starts
+    // at an even slot (16-byte aligned for w8_filter_sum's 128-bit loads)
     std::vector<int> run_of_filter(n_mels + 1, -1);
     for (int r = 0; r < n_runs; r++)
         if (run_g[r] >= 0 && run_g[r] <= n_mels) run_of_filter[run_g[r]] = r;
-    std::vector<int> slot_a(tb.n_segs, 2 * tb.n_segs), slot_b(tb.n_segs, 2 * tb.n_segs);      // default: dump slot
     std::vector<int> f_first(n_mels, 0), f_cnt(n_mels, 0);
+    std::vector<int> slot_a(tb.n_segs, -1), slot_b(tb.n_segs, -1);
     int slot = 0;
     for (int g = 0; g < n_mels; g++) {
+        slot = (slot + 1) & ~1;
         f_first[g] = slot;
         const int rb = g >= 1 ? run_of_filter[g - 1] : -1, ra = run_of_filter[g];
         if (rb >= 0) for (int i = 0; i < seg_cnt[rb]; i++) slot_b[seg_first[rb] + i] = slot++;
         if (ra >= 0) for (int i = 0; i < seg_cnt[ra]; i++) slot_a[seg_first[ra] + i] = slot++;
         f_cnt[g] = slot - f_first[g];
     }
+    const int dump = (slot + 1) & ~1;                     // sums no filter reads (b of the last run, a of run -1) land here
+    tb.seg_slots = dump + 8;                              // + the dump slot and room for the 6-slot reads of the last filter
+    for (int i = 0; i < tb.n_segs; i++) {
+        if (slot_a[i] < 0) slot_a[i] = dump;
+        if (slot_b[i] < 0) slot_b[i] = dump;
+    }
     for (int ci = 0; ci < n_chunks; ci++) {
         const int sg = cflag[ci] >> 8;
         cflag[ci] = (cflag[ci] & 3) | (slot_a[sg] << 8) | (int32_t)((uint32_t)slot_b[sg] << 20);
     }
-    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16 + 2 * tb.n_segs + 2 + n_mels + 32)) + 16;
+    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16 + tb.seg_slots + parts * tb.lm_part + 32)) + 16;
     int32_t *ppos = reinterpret_cast<int32_t *>(blob.data() + tb.ppos);
     for (int w = 0; w < units; w++)
         for (int m = 0; m < 9; m++)
@@ -928,13 +1096,16 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         fdesc[4 * g] = f_first[g];
         fdesc[4 * g + 1] = f_cnt[g];
     }
-    // DCT table, block-major: [block][filter][cw_lanes], zero beyond n_mfcc
+    // DCT table [block][part][q][dct_row]: row (part, q) holds coefficient block * cw_lanes + q for the filters
+    // f = part, part + parts, ...; zero beyond n_mfcc and beyond n_mels
     for (int b = 0; b < dct_blocks; b++)
-        for (int f = 0; f < n_mels; f++)
-            for (int q = 0; q < tb.cw_lanes; q++) {
-                const int cidx = b * tb.cw_lanes + q;
-                blob[tb.dct + (b * n_mels + f) * tb.cw_lanes + q] = cidx < n_mfcc ? (float)h.dct2[(size_t)cidx * n_mels + f] : 0.f;
-            }
+        for (int pt = 0; pt < parts; pt++)
+            for (int q = 0; q < tb.cw_lanes; q++)
+                for (int i = 0; i < tb.dct_row; i++) {
+                    const int cidx = b * tb.cw_lanes + q, f = pt + parts * i;
+                    blob[tb.dct + ((b * 32 + pt * tb.cw_lanes + q) * tb.dct_row) + i] =
+                        (cidx < n_mfcc && f < n_mels && i < tb.lm_part) ? (float)h.dct2[(size_t)cidx * n_mels + f] : 0.f;
+                }
 }
 
 inline size_t warp8_smem_bytes(const W8Tables &tb, int n_mels, int n_warps = W8_WARPS)
@@ -1023,7 +1194,7 @@ inline bool warp8_can_launch(const float *clips, int64_t n_clips, int64_t clip_s
 
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                         int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw = 0,
-                        float2 *stft = nullptr, int stft_pre = 0)
+                        float2 *stft = nullptr, int stft_pre = 0, long long *eacc = nullptr)
 {
     const int64_t pairs = (T + 1) / 2;
     if (!warp8_can_launch(clips, n_clips, clip_stride, T)) {
@@ -1053,7 +1224,12 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.lm_ts = nchw ? 1 : p.n_mels;
     p.lm_fs = nchw ? T : 1;
     p.stft = stft;
+    p.eacc = eacc;
     const int ctas = pl->sm_count;                           // grid size is derived per configuration in w8_launch_cfg
+#ifdef DSPX_W8_LAB
+    // benchmarks/lab/w8_lab.cu: only the headline instantiation, for quick builds of kernel variants
+    return w8_launch_nw<8, true, false, true, W8_WARPS_WIDE>(p, pd->smem_wide, pl->device, std::min<int64_t>(ctas, (p.n_items + W8_WARPS_WIDE - 1) / W8_WARPS_WIDE), st);
+#else
     if (stft) {
         const bool pre = stft_pre && pl->cfg.pre_emphasis > 0.0;
         switch (pd->tb.r1) {
@@ -1070,6 +1246,7 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     }
     set_error("warp8: bad radix");
     return DSPX_EUNSUPPORTED;
+#endif
 }
 #endif
 

@@ -113,6 +113,16 @@ int dspx_features(const dspx_plan *plan, const float *clips_dev, int64_t n_clips
                   int64_t clip_stride, float *logmel_out_dev, float *mfcc_out_dev,
                   float *embed_out_dev, void *stream);
 
+/* Clip embeddings alone (compute_embeddings, src/retrieval/retrieval.py:26-43, without keeping the MFCCs):
+ * the feature kernel adds every frame's coefficients and their squares to per-clip fixed-point accumulators in
+ * workspace_dev (order-independent, so results are reproducible) and a finalize step writes
+ * embed [n_clips, 2*n_mfcc] f32.  No MFCC tensor is written or read.  logmel_out_dev may be NULL.
+ * Needs the warp8 kernel (DSPX_EUNSUPPORTED otherwise: use dspx_features with an MFCC buffer). */
+size_t dspx_embeddings_workspace(const dspx_plan *plan, int64_t n_clips);
+int dspx_embeddings(const dspx_plan *plan, const float *clips_dev, int64_t n_clips, int64_t clip_len,
+                    int64_t clip_stride, float *embed_out_dev, float *logmel_out_dev, void *workspace_dev,
+                    size_t workspace_bytes, void *stream);
+
 /* log-mel written directly in the CNN input layout [n_clips, 1, n_mels, n_frames] that
  * LogMelTransform / train_cnn build with feat.T[None] (src/train/transforms.py:16-18,
  * scripts/models/train_cnn.py:46-47): same values as dspx_features' log-mel, transposed in the

@@ -323,3 +323,38 @@ def test_logmel_batches_feed_the_epoch_loop(torch_cuda):
         opt.step()
         seen += y.size(0)
     assert seen == len(loader.dataset) and bool(torch.isfinite(loss))
+
+
+def test_fused_embeddings_without_mfcc(torch_cuda, clips_5s):
+    """Embeddings alone come from per-clip fixed-point accumulators inside the feature kernel (dspx_embeddings):
+    same values as the statistics of the written MFCCs, reproducible bit for bit, oracle parity."""
+    torch = torch_cuda
+    from dsp_final_b200 import _lib
+    from dsp_final_b200.batch import features_batch
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+    from oracle import oracle as O
+
+    for fl, hop in ((1024, 512), (512, 256), (2048, 1024), (1024, 300)):
+        cfg = MfccConfig(sample_rate=44100, frame_length=fl, hop_length=hop)
+        x = clips_5s[:96]
+        both = features_batch(x, cfg, ("mfcc", "embed"))                 # embed = statistics of the MFCC tensor
+        alone = features_batch(x, cfg, ("embed",))["embed"]              # fused: no MFCC tensor
+        again = features_batch(x, cfg, ("embed", "log_mel"))
+        assert torch.equal(alone, again["embed"]), (fl, hop)             # order-independent accumulation
+        scale = float(both["embed"].abs().max())
+        assert float((alone - both["embed"]).abs().max()) <= 2e-6 * scale, (fl, hop)
+        assert torch.equal(again["log_mel"], features_batch(x, cfg, ("log_mel",))["log_mel"])
+        ref = O.features_batch(x[:3].cpu().numpy(), O.OracleConfig(44100, fl, hop), want=("embed",))["embed"]
+        assert rel_err(alone[:3].cpu().numpy(), ref) < TOL, (fl, hop)
+        host = features_batch(x[:40].cpu().numpy(), cfg, ("embed",))["embed"]      # host pipeline takes the same path
+        assert np.array_equal(host, alone[:40].cpu().numpy()), (fl, hop)
+    # a silent clip: zero variance must come out as zero, not as the square root of round-off
+    cfg = MfccConfig(sample_rate=44100, frame_length=1024, hop_length=512)
+    z = torch.zeros((2, 44_100), device="cuda")
+    e = features_batch(z, cfg, ("embed",))["embed"]
+    assert float(e[:, 13:].abs().max()) < 2e-3 and bool(torch.isfinite(e).all())
+    # the generic kernel has no fused path: the call still works (through an MFCC tensor)
+    g = features_batch(clips_5s[:4], cfg, ("embed",), kernel="generic")["embed"]
+    assert rel_err(g.cpu().numpy(), features_batch(clips_5s[:4], cfg, ("embed",))["embed"].cpu().numpy()) < 1e-5
+    ws = _lib.load().dspx_embeddings_workspace(None, 10)
+    assert ws == 0
