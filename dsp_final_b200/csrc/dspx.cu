@@ -335,7 +335,7 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     const size_t lm_b = (mode == 0 && o_logmel) ? (size_t)T * pl->cfg.n_mels * 4 : 0;
     // embeddings alone: accumulated inside the feature kernel (16 bytes of scratch per coefficient instead of an
     // MFCC tensor); otherwise they are the statistics of the MFCCs that are written anyway
-    const bool fused_embed = mode == 0 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8;
+    const bool fused_embed = mode == 0 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8 && !(clip_len & 1);
     const bool need_mfcc = mode == 0 && (o_mfcc || (o_embed && !fused_embed));
     const size_t mf_b = need_mfcc ? (size_t)T * pl->cfg.n_mfcc * 4 : (fused_embed ? (size_t)pl->cfg.n_mfcc * 16 : 0);
     const size_t em_b = (mode == 0 && o_embed) ? (size_t)2 * pl->cfg.n_mfcc * 4 : 0;

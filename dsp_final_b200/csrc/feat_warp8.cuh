@@ -776,17 +776,24 @@ DSPX_HD float2 w8_dct_partial(const W8Ctx &c, int lane, int c0)
 // Range: |x| < 2^15 over 2^15 frames; resolution 2^-33 per x, 2^-21 per x^2 (std error < 1e-6 for std > 0.01).
 constexpr double W8_EFIX1 = 4294967296.0, W8_EFIX2 = 1048576.0;
 
-DSPX_HD void w8_embed_accumulate(const W8Ctx &c, int q, float2 total)
+// Out of line on the device: the float64 / 64-bit integer code must not take part in the register allocation of
+// the main loop (inlined it cost the headline kernel 36 bytes of spills); it runs once per frame pair on 13 lanes.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void w8_embed_accumulate(long long *eacc, int n_mfcc, int q, float xa, float xb)
 {
-    const double a = (double)total.x, b = c.validB ? (double)total.y : 0.0;
+    const double a = (double)xa, b = (double)xb;
     const long long s1 = (long long)llrint(a * W8_EFIX1) + (long long)llrint(b * W8_EFIX1);
     const long long s2 = (long long)llrint(a * a * W8_EFIX2) + (long long)llrint(b * b * W8_EFIX2);
 #if defined(__CUDA_ARCH__)
-    atomicAdd(reinterpret_cast<unsigned long long *>(c.eacc + q), (unsigned long long)s1);
-    atomicAdd(reinterpret_cast<unsigned long long *>(c.eacc + c.n_mfcc + q), (unsigned long long)s2);
+    atomicAdd(reinterpret_cast<unsigned long long *>(eacc + q), (unsigned long long)s1);
+    atomicAdd(reinterpret_cast<unsigned long long *>(eacc + n_mfcc + q), (unsigned long long)s2);
 #else
-    c.eacc[q] += s1;
-    c.eacc[c.n_mfcc + q] += s2;
+    eacc[q] += s1;
+    eacc[n_mfcc + q] += s2;
 #endif
 }
 
@@ -799,7 +806,7 @@ DSPX_HD void w8_dct_store(const W8Ctx &c, int lane, int c0, float2 total)
             c.mfccA[q] = total.x;
             if (c.validB) c.mfccB[q] = total.y;
         }
-        if (c.eacc) w8_embed_accumulate(c, q, total);
+        if (c.eacc) w8_embed_accumulate(c.eacc, c.n_mfcc, q, total.x, c.validB ? total.y : 0.f);
     }
 }
 
@@ -855,7 +862,9 @@ __device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, in
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-template <int R1, bool PRE, bool STFT, bool SHARE, int NW>
+// EMB: accumulate clip embeddings (w8_embed_accumulate); a template switch so that the plain feature kernels keep
+// their register allocation (the extra pointer alone pushed the 96-register headline variant into spills)
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false>
 __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_warp8_kernel(const W8Params p)
 {
     using G = W8Geo<R1>;
@@ -886,6 +895,7 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     const uint32_t n_warps = gridDim.x * NW;
     for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
+        if (!EMB) c.eacc = nullptr;
         w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8)>(c, lane);
         if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
@@ -1152,12 +1162,12 @@ inline void warp8_release(dspx_plan *pl)
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                             int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
 
-template <int R1, bool PRE, bool STFT, bool SHARE, int NW>
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false>
 inline int w8_launch_nw(const W8Params &p, size_t smem, int device, int64_t ctas, cudaStream_t st)
 {
     static std::atomic<unsigned char> optin[64];
-    DSPX_CUDA_CHECK(optin_max_smem(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW>, optin, device));
-    feat_warp8_kernel<R1, PRE, STFT, SHARE, NW><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
+    DSPX_CUDA_CHECK(optin_max_smem(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB>, optin, device));
+    feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
 }
@@ -1169,11 +1179,14 @@ inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, in
     if (!STFT && R1 != 16 && pd->smem_wide) {
         int64_t ctas = ((int64_t)p.n_items + W8_WARPS_WIDE - 1) / W8_WARPS_WIDE;
         if (ctas > sm_count) ctas = sm_count;
-        return w8_launch_nw<R1, PRE, STFT, SHARE, (R1 != 16 && !STFT) ? W8_WARPS_WIDE : W8_WARPS>(p, pd->smem_wide, device, ctas, st);
+        constexpr int NWW = (R1 != 16 && !STFT) ? W8_WARPS_WIDE : W8_WARPS;
+        if (!STFT && p.eacc) return w8_launch_nw<R1, PRE, STFT, SHARE, NWW, !STFT>(p, pd->smem_wide, device, ctas, st);
+        return w8_launch_nw<R1, PRE, STFT, SHARE, NWW>(p, pd->smem_wide, device, ctas, st);
     }
     int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
     const int64_t resident = (int64_t)sm_count * pd->ctas_per_sm;
     if (ctas > resident) ctas = resident;
+    if (!STFT && p.eacc) return w8_launch_nw<R1, PRE, STFT, SHARE, W8_WARPS, !STFT>(p, pd->smem, device, ctas, st);
     return w8_launch_nw<R1, PRE, STFT, SHARE, W8_WARPS>(p, pd->smem, device, ctas, st);
 }
 
