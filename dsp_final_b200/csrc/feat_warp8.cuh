@@ -37,7 +37,11 @@ constexpr int W8_WARPS = 8;               // warps per CTA, two CTAs per SM (128
 #ifndef DSPX_W8_WIDE
 #define DSPX_W8_WIDE 20
 #endif
-constexpr int W8_WARPS_WIDE = DSPX_W8_WIDE;         // or one 20-warp CTA per SM (<= 102 registers): more warps in flight to
+constexpr int W8_WARPS_WIDE = DSPX_W8_WIDE;
+#ifndef DSPX_W8_R16
+#define DSPX_W8_R16 10
+#endif
+constexpr int W8_WARPS_R16 = DSPX_W8_R16;           // n_fft 2048: one CTA per SM with as many 16 KB tiles as fit beside the tables         // or one 20-warp CTA per SM (<= 102 registers): more warps in flight to
                                           // cover the shared-memory pipe; +6 % on the feature path, worse for STFT mode
 
 
@@ -1129,6 +1133,7 @@ struct W8PlanData {
     int ctas_per_sm;
     size_t smem;
     size_t smem_wide;        // 0 when the 20-warp configuration does not fit
+    size_t smem_r16;         // n_fft 2048: shared memory of the W8_WARPS_R16-warp configuration, 0 when it does not fit
     bool share;              // hop == n_fft / 2: the two frames of a pair share rows (DSPX_W8_NOSHARE=1 at plan creation disables)
 };
 
@@ -1145,6 +1150,8 @@ inline int warp8_prepare(dspx_plan *pl)
     pd->ctas_per_sm = (tb.r1 != 16 && smem * 2 + 2048 <= 227 * 1024) ? 2 : 1;
     const size_t wide = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_WIDE);
     pd->smem_wide = (tb.r1 != 16 && wide + 1024 <= 227 * 1024 && !getenv("DSPX_W8_NARROW")) ? wide : 0;
+    const size_t r16 = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_R16);
+    pd->smem_r16 = (tb.r1 == 16 && W8_WARPS_R16 > W8_WARPS && r16 + 1024 <= 227 * 1024) ? r16 : 0;
     pd->share = (2 * pl->cfg.hop_length == pl->P) && !getenv("DSPX_W8_NOSHARE");
     pl->fast_host = pd;
     DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));
@@ -1182,6 +1189,13 @@ inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, in
         constexpr int NWW = (R1 != 16 && !STFT) ? W8_WARPS_WIDE : W8_WARPS;
         if (!STFT && p.eacc) return w8_launch_nw<R1, PRE, STFT, SHARE, NWW, !STFT>(p, pd->smem_wide, device, ctas, st);
         return w8_launch_nw<R1, PRE, STFT, SHARE, NWW>(p, pd->smem_wide, device, ctas, st);
+    }
+    if (!STFT && R1 == 16 && pd->smem_r16) {
+        int64_t ctas = ((int64_t)p.n_items + W8_WARPS_R16 - 1) / W8_WARPS_R16;
+        if (ctas > sm_count) ctas = sm_count;
+        constexpr int NWR = (R1 == 16 && !STFT) ? W8_WARPS_R16 : W8_WARPS;
+        if (p.eacc) return w8_launch_nw<R1, PRE, STFT, SHARE, NWR, !STFT>(p, pd->smem_r16, device, ctas, st);
+        return w8_launch_nw<R1, PRE, STFT, SHARE, NWR>(p, pd->smem_r16, device, ctas, st);
     }
     int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
     const int64_t resident = (int64_t)sm_count * pd->ctas_per_sm;
