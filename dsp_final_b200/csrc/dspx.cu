@@ -865,14 +865,15 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     const bool prefilter = !want_f64 && !use_tc && f32_ok;
 
     if (use_tc) {
-        DSPX_CUDA_CHECK(cudaMemsetAsync(qf_t, 0, qf_bytes, st));              // zero padding: columns >= dim, rows >= n
-        DSPX_CUDA_CHECK(cudaMemsetAsync(dbf_t, 0, dbf_bytes, st));
+        // the kernel writes the zero padding too (columns >= dim, rows up to the tile multiple): no memset pass
+        const int64_t nq_pad = (nq + TC_QT - 1) / TC_QT * TC_QT, ndb_pad = (ndb + TK_ROWS - 1) / TK_ROWS * TK_ROWS;
+        const unsigned gq = (unsigned)((nq_pad + NR_ROWS - 1) / NR_ROWS), gd = (unsigned)((ndb_pad + NR_ROWS - 1) / NR_ROWS);
         if (dtype == DSPX_DTYPE_F32) {
-            normalize_rows_pad32_kernel<float><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((const float *)q_dev, nq, dim, qn, qf_t);
-            normalize_rows_pad32_kernel<float><<<(unsigned)((ndb + 127) / 128), 128, 0, st>>>((const float *)db_dev, ndb, dim, dbn, dbf_t);
+            normalize_rows_pad32_kernel<float><<<gq, 128, 0, st>>>((const float *)q_dev, nq, nq_pad, dim, qn, qf_t);
+            normalize_rows_pad32_kernel<float><<<gd, 128, 0, st>>>((const float *)db_dev, ndb, ndb_pad, dim, dbn, dbf_t);
         } else {
-            normalize_rows_pad32_kernel<double><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((const double *)q_dev, nq, dim, qn, qf_t);
-            normalize_rows_pad32_kernel<double><<<(unsigned)((ndb + 127) / 128), 128, 0, st>>>((const double *)db_dev, ndb, dim, dbn, dbf_t);
+            normalize_rows_pad32_kernel<double><<<gq, 128, 0, st>>>((const double *)q_dev, nq, nq_pad, dim, qn, qf_t);
+            normalize_rows_pad32_kernel<double><<<gd, 128, 0, st>>>((const double *)db_dev, ndb, ndb_pad, dim, dbn, dbf_t);
         }
     } else
     if (prefilter) {

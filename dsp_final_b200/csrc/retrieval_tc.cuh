@@ -48,24 +48,49 @@ constexpr double TC_EPS = 8e-6;
 constexpr int TC_FIFO = 8, TC_FIFO_TRIGGER = 4;   // pending candidates per query: ring size / drain trigger
 constexpr int TC_MAX_K = 28;          // the per-thread lists ([k][256] doubles + ints) share smem with the tiles
 
+// Rows scaled by 1 / (||row|| + 1e-10) in float64 (src/retrieval/retrieval.py:46-48: the division, not a multiply by
+// the reciprocal; the norm is the same left-to-right fma chain as normalize_rows_kernel, so out64 is bit-identical
+// to it) plus the zero-padded float32 copy [n_pad][32] the tensor-core filter reads.  A CTA owns NR_ROWS consecutive
+// rows: they are one contiguous span of the input and of both outputs, so every global access is coalesced (the
+// round-1 kernel had one thread walk one row: 26 strided stores per thread, 9x the HBM time of the copy).
+constexpr int NR_ROWS = 64;
+
 template <typename T>
-__global__ void normalize_rows_pad32_kernel(const T *x, int64_t n, int dim, double *out64, float *out32)
+__global__ void __launch_bounds__(128) normalize_rows_pad32_kernel(const T *x, int64_t n, int64_t n_pad, int dim,
+                                                                  double *out64, float *out32)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const T *row = x + (size_t)r * dim;
-    double s = 0.0;
-    for (int c = 0; c < dim; c++) {
-        const double v = (double)row[c];
-        s = fma(v, v, s);
+    __shared__ T s_in[NR_ROWS * TC_KPAD];
+    __shared__ float s_f32[NR_ROWS * TC_KPAD];
+    __shared__ double s_inv[NR_ROWS];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * NR_ROWS;
+    const int64_t rows = (n - r0) < NR_ROWS ? ((n - r0) > 0 ? (n - r0) : 0) : NR_ROWS;      // real rows of this CTA
+    const int64_t elems = rows * dim;
+    const T *src = x + (size_t)r0 * dim;
+    for (int64_t e = tid; e < elems; e += 128) s_in[e] = src[e];
+    for (int e = tid; e < NR_ROWS * TC_KPAD; e += 128) s_f32[e] = 0.f;                     // padding columns and rows
+    __syncthreads();
+    if (tid < rows) {
+        double s = 0.0;
+        for (int c = 0; c < dim; c++) {
+            const double v = (double)s_in[tid * dim + c];
+            s = fma(v, v, s);
+        }
+        s_inv[tid] = sqrt(s) + 1e-10;
     }
-    const double inv = sqrt(s) + 1e-10;
-    float *t = out32 + (size_t)r * TC_KPAD;
-    for (int c = 0; c < dim; c++) {
-        const double v = (double)row[c] / inv;
-        out64[(size_t)r * dim + c] = v;
-        t[c] = (float)v;
+    __syncthreads();
+    double *dst = out64 + (size_t)r0 * dim;
+    for (int64_t e = tid; e < elems; e += 128) {
+        const int r = (int)(e / dim), c = (int)(e - (int64_t)r * dim);
+        const double v = (double)s_in[e] / s_inv[r];
+        dst[e] = v;
+        s_f32[r * TC_KPAD + c] = (float)v;
     }
+    __syncthreads();
+    const int64_t pad_rows = (n_pad - r0) < NR_ROWS ? (n_pad - r0) : NR_ROWS;
+    float4 *d32 = reinterpret_cast<float4 *>(out32 + (size_t)r0 * TC_KPAD);
+    const float4 *s32 = reinterpret_cast<const float4 *>(s_f32);
+    for (int e = tid; e < pad_rows * (TC_KPAD / 4); e += 128) d32[e] = s32[e];
 }
 
 #ifdef DSPX_TC_PROFILE

@@ -108,13 +108,14 @@ def sharded_retrieval(local_db_emb, local_db_targets, local_q_emb, local_q_targe
     """
     import torch
 
+    k_list = [int(k) for k in k_list]
+    on_gpu = isinstance(local_q_emb, torch.Tensor) and local_q_emb.is_cuda
+    fast_hits = hits_fn is None and on_gpu          # hit counters stay on the device: one all-reduce, one host read
     if topk_fn is None or hits_fn is None:
         from . import retrieval as R
 
         topk_fn = topk_fn or R.cosine_topk
         hits_fn = hits_fn or R.hits_at_k
-    k_list = [int(k) for k in k_list]
-    on_gpu = isinstance(local_q_emb, torch.Tensor) and local_q_emb.is_cuda
     marks = []
 
     def mark():
@@ -130,10 +131,22 @@ def sharded_retrieval(local_db_emb, local_db_targets, local_q_emb, local_q_targe
     kmax = min(max(k_list), db.shape[0])
     idx = topk_fn(local_q_emb, db, kmax)
     mark()
-    hits = [hits_fn(idx, min(k, kmax), tdb, local_q_targets) for k in k_list]
-    dev = local_q_emb.device if isinstance(local_q_emb, torch.Tensor) else None
-    tot = all_reduce_sum_ints(hits + [int(local_q_emb.shape[0])], device=dev)
-    mark()
+    if fast_hits:
+        import torch.distributed as dist
+
+        from .retrieval import hits_at_k_device
+
+        counts = hits_at_k_device(idx, [min(k, kmax) for k in k_list], tdb, local_q_targets)
+        t = torch.cat([counts, torch.tensor([int(local_q_emb.shape[0])], dtype=torch.int64, device=counts.device)])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        mark()
+        tot = [int(v) for v in t.tolist()]
+    else:
+        hits = [hits_fn(idx, min(k, kmax), tdb, local_q_targets) for k in k_list]
+        dev = local_q_emb.device if isinstance(local_q_emb, torch.Tensor) else None
+        tot = all_reduce_sum_ints(hits + [int(local_q_emb.shape[0])], device=dev)
+        mark()
     if profile is not None:
         profile["db_rows"] = int(db.shape[0])
         profile["gather_bytes"] = int((db.shape[0] - local_db_emb.shape[0]) * (db.shape[1] * db.element_size() + tdb.element_size()))

@@ -176,6 +176,28 @@ def cosine_similarity(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return out.cpu().numpy() if host else out
 
 
+def hits_at_k_device(topk_idx, k_list, targets_db, targets_query):
+    """Device-side hit counts for several k at once: int64 tensor [len(k_list)] on the GPU, no host sync.
+
+    topk_idx [nq, kmax] int32, targets_db [ndb] and targets_query [nq] int32 -- torch CUDA tensors.
+    """
+    import torch
+
+    idx = topk_idx.to(torch.int32).contiguous()
+    tdb = targets_db.to(torch.int32).contiguous()
+    tq = targets_query.to(torch.int32).contiguous()
+    dev = idx.device
+    with torch.cuda.device(dev.index):
+        hits = torch.zeros(len(k_list), dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev.index).cuda_stream
+        for i, k in enumerate(k_list):
+            if k > idx.shape[1]:
+                raise ValueError("k exceeds the width of topk_idx")
+            _lib.check(_lib.load().dspx_hits_at_k(idx.data_ptr(), idx.shape[0], idx.shape[1], int(k), tdb.data_ptr(),
+                                                  tq.data_ptr(), hits[i:].data_ptr(), st), "dspx_hits_at_k")
+    return hits
+
+
 def hits_at_k(topk_idx, k: int, targets_db, targets_query) -> int:
     """Number of queries with at least one same-target row in their top k (retrieval.py:66-70)."""
     import torch
