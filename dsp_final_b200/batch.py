@@ -98,7 +98,7 @@ def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int
         t = plan.num_frames(length)
         # embeddings without MFCCs: accumulated inside the feature kernel (no [B, T, n_mfcc] tensor at all)
         fused = ("embed" in want and "mfcc" not in want and plan.kernel == "warp8"
-                 and x.data_ptr() % 8 == 0 and x.stride(0) % 2 == 0)
+                 and x.data_ptr() % 8 == 0 and x.stride(0) % 2 == 0 and plan.hop_length % 2 == 0)
         need_mfcc = "mfcc" in want or ("embed" in want and not fused)
         with torch.cuda.device(dev):
             out = {}

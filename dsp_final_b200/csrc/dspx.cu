@@ -196,7 +196,8 @@ static int features_device(const dspx_plan *pl, const float *clips, int64_t n_cl
     if (T < 0) return DSPX_EINVAL;
     int rc;
     if (embed && !mfcc) {
-        if (!eacc || pl->kernel != DSPX_KERNEL_WARP8 || !warp8_can_launch(clips, n_clips, clip_stride, T)) {
+        if (!eacc || pl->kernel != DSPX_KERNEL_WARP8 || !warp8_can_launch(clips, n_clips, clip_stride, T) ||
+            !warp8_aligned(pl, clips, clip_stride)) {
             set_error("embeddings without an MFCC buffer need the warp8 kernel and 8-byte aligned clips with an even stride");
             return DSPX_EUNSUPPORTED;
         }
@@ -223,7 +224,8 @@ static int features_device(const dspx_plan *pl, const float *clips, int64_t n_cl
 static int stft_device(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
                        int64_t T, int pre, float2 *out, cudaStream_t st)
 {
-    if (pl->kernel == DSPX_KERNEL_WARP8 && pl->take_stft == pl->P && warp8_can_launch(clips, n_clips, clip_stride, T))
+    if (pl->kernel == DSPX_KERNEL_WARP8 && pl->take_stft == pl->P && warp8_can_launch(clips, n_clips, clip_stride, T) &&
+        warp8_aligned(pl, clips, clip_stride))
         return launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, nullptr, nullptr, st, 0, out, pre);
     return launch_generic(pl, clips, n_clips, clip_len, clip_stride, T, pl->take_stft, pre, nullptr, nullptr, out, st);
 }
@@ -335,7 +337,8 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     const size_t lm_b = (mode == 0 && o_logmel) ? (size_t)T * pl->cfg.n_mels * 4 : 0;
     // embeddings alone: accumulated inside the feature kernel (16 bytes of scratch per coefficient instead of an
     // MFCC tensor); otherwise they are the statistics of the MFCCs that are written anyway
-    const bool fused_embed = mode == 0 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8 && !(clip_len & 1);
+    const bool fused_embed = mode == 0 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8 && !(clip_len & 1) &&
+                             !(pl->cfg.hop_length & 1);
     const bool need_mfcc = mode == 0 && (o_mfcc || (o_embed && !fused_embed));
     const size_t mf_b = need_mfcc ? (size_t)T * pl->cfg.n_mfcc * 4 : (fused_embed ? (size_t)pl->cfg.n_mfcc * 16 : 0);
     const size_t em_b = (mode == 0 && o_embed) ? (size_t)2 * pl->cfg.n_mfcc * 4 : 0;

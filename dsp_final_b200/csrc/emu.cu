@@ -153,7 +153,9 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     pl.n_bins = e.n_bins;
     pl.host = e.t;
     if (!warp8_supported(&pl) || clip_len < cfg->frame_length) return DSPX_EUNSUPPORTED;
-    if (clip_stride & 1) return DSPX_EUNSUPPORTED;
+    // frames off the 8-byte grid replay the 4-byte-load variant, like launch_warp8 picks it
+    const bool u4 = (clip_stride & 1) || (cfg->hop_length & 1) || (reinterpret_cast<uintptr_t>(clips) & 7);
+    if (u4 && stft_out) return DSPX_EUNSUPPORTED;
     std::vector<float> blob;
     W8Tables tb{};
     warp8_build_tables(&pl, blob, tb);
@@ -196,15 +198,16 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     const int units = r1 >= 8 ? r1 / 8 : 1;
     std::vector<W8Power> pw(32 * 2);
     // the device kernel computes window / twiddles on the feature path and loads them in STFT mode: replay the same
-#define W8_P1(R, PRE_, SH_) do { if (p.stft) w8_pass1<R, PRE_, SH_, false>(c, lane); else w8_pass1<R, PRE_, SH_, true>(c, lane); } while (0)
+#define W8_P1(R, PRE_, SH_) do { if (p.stft) w8_pass1<R, PRE_, SH_, false>(c, lane); else if (u4) w8_pass1<R, PRE_, false, true, true>(c, lane); else w8_pass1<R, PRE_, SH_, true>(c, lane); } while (0)
     for (uint32_t item = 0; item < p.n_items; item++) {
         w8_set_item(p, c, item);
         for (int lane = 0; lane < 32; lane++) {
-            const bool share = 2 * cfg->hop_length == e.P && r1 != 16;
+            const bool share = 2 * cfg->hop_length == e.P && r1 != 16 && !u4;
             if (r1 == 4 && share) { if (pre) W8_P1(4, true, true); else W8_P1(4, false, true); }
             else if (r1 == 4) { if (pre) W8_P1(4, true, false); else W8_P1(4, false, false); }
             else if (r1 == 8 && share) { if (pre) W8_P1(8, true, true); else W8_P1(8, false, true); }
             else if (r1 == 8) { if (pre) W8_P1(8, true, false); else W8_P1(8, false, false); }
+            else if (u4) { if (pre) w8_pass1<16, true, false, false, true>(c, lane); else w8_pass1<16, false, false, false, true>(c, lane); }
             else { if (pre) w8_pass1<16, true, false, false>(c, lane); else w8_pass1<16, false, false, false>(c, lane); }
         }
         for (int lane = 0; lane < 32; lane++) {

@@ -320,7 +320,9 @@ template <int R1, bool TRIG, class Trig> DSPX_HD float2 w8_twiddle_of(const W8Ct
 // sample without a predecessor is sample 0 of a clip (y[0] = x[0], src/dsp/mfcc.py:88).
 // TRIG: window and twiddles computed (feature path, R1 <= 8) instead of loaded (STFT mode is HBM-bound and keeps
 // the loads: the extra instructions cost it 2 %; R1 = 16 has no registers to spare)
-template <int R1, bool PRE, bool SHARE, bool TRIG>
+// U4: frames need not start on an 8-byte boundary (odd hop, odd clip stride, unaligned base): the two samples of a
+// lane are fetched with two 4-byte loads instead of one 8-byte load (never combined with SHARE, whose hop is even).
+template <int R1, bool PRE, bool SHARE, bool TRIG, bool U4 = false>
 DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 {
     if (SHARE) {
@@ -390,8 +392,13 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
         float pva[R1], pvb[R1];
 #pragma unroll
         for (int a = 0; a < R1; a++) {
-            xa[a] = *reinterpret_cast<const float2 *>(pa + 128 * a);
-            xb[a] = *reinterpret_cast<const float2 *>(pb + 128 * a);
+            if (U4) {
+                xa[a] = make_float2(pa[128 * a], pa[128 * a + 1]);
+                xb[a] = make_float2(pb[128 * a], pb[128 * a + 1]);
+            } else {
+                xa[a] = *reinterpret_cast<const float2 *>(pa + 128 * a);
+                xb[a] = *reinterpret_cast<const float2 *>(pb + 128 * a);
+            }
         }
         if (PRE) {
             const bool edgeA = c.firstA && tid == 0, edgeB = c.firstB && tid == 0;
@@ -868,7 +875,7 @@ __device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, in
 
 // EMB: accumulate clip embeddings (w8_embed_accumulate); a template switch so that the plain feature kernels keep
 // their register allocation (the extra pointer alone pushed the 96-register headline variant into spills)
-template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false>
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false, bool U4 = false>
 __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_warp8_kernel(const W8Params p)
 {
     using G = W8Geo<R1>;
@@ -900,7 +907,7 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
         if (!EMB) c.eacc = nullptr;
-        w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8)>(c, lane);
+        w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8), U4>(c, lane);
         if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
 #if !defined(DSPX_ABL) || DSPX_ABL != 5
@@ -969,7 +976,7 @@ inline int warp8_radix(const dspx_plan *pl) { return pl->P == 512 ? 4 : (pl->P =
 
 inline bool warp8_supported(const dspx_plan *pl)
 {
-    return warp8_radix(pl) != 0 && pl->cfg.frame_length == pl->P && (pl->cfg.hop_length % 2) == 0 &&
+    return warp8_radix(pl) != 0 && pl->cfg.frame_length == pl->P &&
            pl->cfg.n_mels <= 256 && pl->cfg.n_mfcc <= 128 && pl->host.two_band_ok;
 }
 
@@ -1169,12 +1176,12 @@ inline void warp8_release(dspx_plan *pl)
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                             int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
 
-template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false>
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false, bool U4 = false>
 inline int w8_launch_nw(const W8Params &p, size_t smem, int device, int64_t ctas, cudaStream_t st)
 {
     static std::atomic<unsigned char> optin[64];
-    DSPX_CUDA_CHECK(optin_max_smem(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB>, optin, device));
-    feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
+    DSPX_CUDA_CHECK(optin_max_smem(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB, U4>, optin, device));
+    feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB, U4><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
 }
@@ -1204,6 +1211,26 @@ inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, in
     return w8_launch_nw<R1, PRE, STFT, SHARE, W8_WARPS>(p, pd->smem, device, ctas, st);
 }
 
+// features from frames that are not 8-byte aligned: 4-byte sample loads, no row sharing, no fused embeddings
+template <int R1, bool PRE>
+inline int w8_launch_u4(const W8Params &p, const W8PlanData *pd, int device, int sm_count, cudaStream_t st)
+{
+    if (R1 != 16 && pd->smem_wide) {
+        int64_t ctas = ((int64_t)p.n_items + W8_WARPS_WIDE - 1) / W8_WARPS_WIDE;
+        if (ctas > sm_count) ctas = sm_count;
+        return w8_launch_nw<R1, PRE, false, false, (R1 != 16) ? W8_WARPS_WIDE : W8_WARPS, false, true>(p, pd->smem_wide, device, ctas, st);
+    }
+    if (R1 == 16 && pd->smem_r16) {
+        int64_t ctas = ((int64_t)p.n_items + W8_WARPS_R16 - 1) / W8_WARPS_R16;
+        if (ctas > sm_count) ctas = sm_count;
+        return w8_launch_nw<R1, PRE, false, false, (R1 == 16) ? W8_WARPS_R16 : W8_WARPS, false, true>(p, pd->smem_r16, device, ctas, st);
+    }
+    int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
+    const int64_t resident = (int64_t)sm_count * pd->ctas_per_sm;
+    if (ctas > resident) ctas = resident;
+    return w8_launch_nw<R1, PRE, false, false, W8_WARPS, false, true>(p, pd->smem, device, ctas, st);
+}
+
 template <int R1, bool PRE, bool STFT>
 inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, int sm_count, cudaStream_t st)
 {
@@ -1213,10 +1240,19 @@ inline int w8_launch_one(const W8Params &p, const W8PlanData *pd, int device, in
     return w8_launch_cfg<R1, PRE, STFT, false>(p, pd, device, sm_count, st);
 }
 
-// 8-byte vector loads need even row strides and an 8-byte aligned base; items are 32-bit
+// items are 32-bit
 inline bool warp8_can_launch(const float *clips, int64_t n_clips, int64_t clip_stride, int64_t T)
 {
-    return !(clip_stride & 1) && !(reinterpret_cast<uintptr_t>(clips) & 7) && n_clips * ((T + 1) / 2) < (int64_t)0x7fffffff;
+    (void)clips;
+    (void)clip_stride;
+    return n_clips * ((T + 1) / 2) < (int64_t)0x7fffffff;
+}
+
+// 8-byte vector loads (and with them row sharing, the STFT mode and the fused embeddings) need every frame to start on
+// an 8-byte boundary: even hop, even row stride, aligned base
+inline bool warp8_aligned(const dspx_plan *pl, const float *clips, int64_t clip_stride)
+{
+    return !(pl->cfg.hop_length & 1) && !(clip_stride & 1) && !(reinterpret_cast<uintptr_t>(clips) & 7);
 }
 
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
@@ -1224,8 +1260,9 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
                         float2 *stft = nullptr, int stft_pre = 0, long long *eacc = nullptr)
 {
     const int64_t pairs = (T + 1) / 2;
-    if (!warp8_can_launch(clips, n_clips, clip_stride, T)) {
-        if (stft) { set_error("warp8 stft: unaligned clips"); return DSPX_EUNSUPPORTED; }
+    const bool aligned = warp8_aligned(pl, clips, clip_stride);
+    if (!warp8_can_launch(clips, n_clips, clip_stride, T) || (!aligned && (stft || eacc))) {
+        if (stft || eacc) { set_error("warp8 stft / fused embeddings: unaligned clips or batch too large"); return DSPX_EUNSUPPORTED; }
         return launch_generic_fallback(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
     }
     const W8PlanData *pd = static_cast<const W8PlanData *>(pl->fast_host);
@@ -1266,6 +1303,13 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
         }
     }
     const bool pre = pl->cfg.pre_emphasis > 0.0;
+    if (!aligned) {
+        switch (pd->tb.r1) {
+            case 4: return pre ? w8_launch_u4<4, true>(p, pd, pl->device, ctas, st) : w8_launch_u4<4, false>(p, pd, pl->device, ctas, st);
+            case 8: return pre ? w8_launch_u4<8, true>(p, pd, pl->device, ctas, st) : w8_launch_u4<8, false>(p, pd, pl->device, ctas, st);
+            case 16: return pre ? w8_launch_u4<16, true>(p, pd, pl->device, ctas, st) : w8_launch_u4<16, false>(p, pd, pl->device, ctas, st);
+        }
+    }
     switch (pd->tb.r1) {
         case 4: return pre ? w8_launch_one<4, true, false>(p, pd, pl->device, ctas, st) : w8_launch_one<4, false, false>(p, pd, pl->device, ctas, st);
         case 8: return pre ? w8_launch_one<8, true, false>(p, pd, pl->device, ctas, st) : w8_launch_one<8, false, false>(p, pd, pl->device, ctas, st);

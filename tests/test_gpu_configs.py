@@ -358,3 +358,31 @@ def test_fused_embeddings_without_mfcc(torch_cuda, clips_5s):
     assert rel_err(g.cpu().numpy(), features_batch(clips_5s[:4], cfg, ("embed",))["embed"].cpu().numpy()) < 1e-5
     ws = _lib.load().dspx_embeddings_workspace(None, 10)
     assert ws == 0
+
+
+def test_unaligned_frames_stay_on_the_fast_kernel(torch_cuda):
+    """Odd hop (441 samples = 10 ms) or an odd row stride: the warp8 kernel's 4-byte-load variant, oracle parity;
+    same results as the aligned variant when both apply."""
+    torch = torch_cuda
+    from dsp_final_b200 import synth
+    from dsp_final_b200.batch import features_batch
+    from dsp_final_b200.dsp.mfcc import MfccConfig
+    from dsp_final_b200.plan import get_plan
+    from oracle import oracle as O
+
+    host = synth.host_clips(6, seed=23, length=66_151)                        # odd length -> odd stride
+    dev = torch.as_tensor(host).cuda()
+    for fl, hop in ((1024, 441), (512, 147), (2048, 441), (1024, 512)):
+        cfg = MfccConfig(sample_rate=44100, frame_length=fl, hop_length=hop)
+        assert get_plan(cfg).kernel == "warp8"
+        out = features_batch(dev, cfg, ("mfcc", "log_mel", "embed"))
+        ref = O.features_batch(host, O.OracleConfig(44100, fl, hop))
+        for name in ("mfcc", "log_mel", "embed"):
+            assert rel_err(out[name].cpu().numpy(), ref[name]) < TOL, (fl, hop, name)
+    # even hop, even stride: aligned and unaligned variants compute the same frames (offset the base by one sample)
+    cfg = MfccConfig(sample_rate=44100, frame_length=1024, hop_length=512)
+    wide = torch.zeros((4, 66_152), device="cuda")
+    wide[:, 1:] = dev[:4, :66_151]
+    a = features_batch(dev[:4, :66_150].contiguous(), cfg, ("mfcc",))["mfcc"]
+    b = features_batch(wide[:, 1:66_151], cfg, ("mfcc",))["mfcc"]             # base pointer 4 bytes off the grid
+    assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-6

@@ -171,6 +171,28 @@ def test_warp8_kernel_replay_matches_reference(built, golden_small):
     assert covered >= 15
 
 
+def test_warp8_replay_unaligned_frames(built):
+    """Odd hops and odd row strides put frames off the 8-byte grid: the 4-byte-load variant of the warp8 kernel
+    (U4) against the oracle, n_fft 512 / 1024 / 2048 (hop 441 = 10 ms at 44.1 kHz is a common setting)."""
+    from dsp_final_b200 import synth
+    from oracle import oracle as O
+
+    lib, DspxConfig = _emu(built)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    for fl, hop, length in ((1024, 441, 12_001), (512, 147, 9_000), (2048, 441, 16_385), (1024, 512, 12_001)):
+        x = np.ascontiguousarray(synth.host_clips(2, seed=17, length=length))
+        m = dict(sample_rate=44100, frame_length=fl, hop_length=hop, n_fft=None, n_mels=40, n_mfcc=13, f_min=0.0,
+                 f_max=None, pre_emphasis=0.97, window="hann")
+        cfg = _cfg_struct(DspxConfig, m, kernel=2)
+        t = 1 + (length - fl) // hop
+        lm = np.zeros((2, t, 40), np.float32)
+        mf = np.zeros((2, t, 13), np.float32)
+        rc = lib.emu_features_warp8(C.byref(cfg), fp(x), C.c_int64(2), C.c_int64(length), C.c_int64(length), fp(lm), fp(mf), None, 0)
+        assert rc == 0, (fl, hop)
+        ref = O.features_batch(x, O.OracleConfig(44100, fl, hop), want=("mfcc", "log_mel"))
+        assert rel_err(mf, ref["mfcc"]) < 1e-5 and rel_err(lm, ref["log_mel"]) < 1e-5, (fl, hop)
+
+
 def test_warp8_replay_full_clip(built, golden_config1):
     lib, DspxConfig = _emu(built)
     g = golden_config1
