@@ -154,7 +154,8 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     pl.host = e.t;
     if (!warp8_supported(&pl) || clip_len < cfg->frame_length) return DSPX_EUNSUPPORTED;
     // frames off the 8-byte grid replay the 4-byte-load variant, like launch_warp8 picks it
-    const bool u4 = (clip_stride & 1) || (cfg->hop_length & 1) || (reinterpret_cast<uintptr_t>(clips) & 7);
+    const bool u4 = (clip_stride & 1) || (cfg->hop_length & 1) || (reinterpret_cast<uintptr_t>(clips) & 7) ||
+                    cfg->frame_length != e.P;
     if (u4 && stft_out) return DSPX_EUNSUPPORTED;
     std::vector<float> blob;
     W8Tables tb{};
@@ -194,11 +195,12 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     c.cw_lanes = tb.cw_lanes;
     c.dct_row = tb.dct_row;
     c.lm_part = tb.lm_part;
+    c.take = cfg->frame_length < e.P ? cfg->frame_length : e.P;
     const int r1 = tb.r1;
     const int units = r1 >= 8 ? r1 / 8 : 1;
     std::vector<W8Power> pw(32 * 2);
     // the device kernel computes window / twiddles on the feature path and loads them in STFT mode: replay the same
-#define W8_P1(R, PRE_, SH_) do { if (p.stft) w8_pass1<R, PRE_, SH_, false>(c, lane); else if (u4) w8_pass1<R, PRE_, false, true, true>(c, lane); else w8_pass1<R, PRE_, SH_, true>(c, lane); } while (0)
+#define W8_P1(R, PRE_, SH_) do { if (p.stft) w8_pass1<R, PRE_, SH_, false>(c, lane); else if (u4) w8_pass1<R, PRE_, false, false, true>(c, lane); else w8_pass1<R, PRE_, SH_, true>(c, lane); } while (0)
     for (uint32_t item = 0; item < p.n_items; item++) {
         w8_set_item(p, c, item);
         for (int lane = 0; lane < 32; lane++) {

@@ -199,7 +199,7 @@ struct W8Params {
     const float *clips;
     int64_t n_clips, clip_stride, n_frames;
     uint32_t pairs_per_clip, n_items;
-    int hop, n_mels, n_mfcc, prefetch, share;
+    int hop, n_mels, n_mfcc, prefetch, share, take;
     float alpha;
     float win_a, win_b;      // see W8Ctx
     W8Tables tb;
@@ -224,6 +224,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     float alpha;
     float win_a, win_b;      // 0.5 w[n] = win_a + win_b cos(2 pi n / P): hann (0.25, -0.25), hamming (0.27, -0.23), rect (0.5, 0)
     int n_mels, n_mfcc, rounds, cw_lanes, dct_row, lm_part, validB;
+    int take;                // samples of a frame that enter the transform (= n_fft except in the general variant)
     float *logmelA, *logmelB, *mfccA, *mfccB;   // rows of the two frames (null when not requested)
     int64_t lm_fs;
     float2 *stftA, *stftB;   // STFT mode: rows of the two frames
@@ -320,8 +321,10 @@ template <int R1, bool TRIG, class Trig> DSPX_HD float2 w8_twiddle_of(const W8Ct
 // sample without a predecessor is sample 0 of a clip (y[0] = x[0], src/dsp/mfcc.py:88).
 // TRIG: window and twiddles computed (feature path, R1 <= 8) instead of loaded (STFT mode is HBM-bound and keeps
 // the loads: the extra instructions cost it 2 %; R1 = 16 has no registers to spare)
-// U4: frames need not start on an 8-byte boundary (odd hop, odd clip stride, unaligned base): the two samples of a
-// lane are fetched with two 4-byte loads instead of one 8-byte load (never combined with SHARE, whose hop is even).
+// U4, the general variant: frames need not start on an 8-byte boundary (odd hop, odd clip stride, unaligned base) and
+// may be shorter than the transform (frame_length < n_fft: zero padding, src/dsp/fft.py:34-36) or longer (truncation,
+// fft.py:32-33).  The two samples of a lane are fetched with two 4-byte loads, each only if it lies inside the
+// first c.take samples of the frame; the window comes from the table (zero past take).  Never combined with SHARE.
 template <int R1, bool PRE, bool SHARE, bool TRIG, bool U4 = false>
 DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 {
@@ -393,8 +396,9 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 #pragma unroll
         for (int a = 0; a < R1; a++) {
             if (U4) {
-                xa[a] = make_float2(pa[128 * a], pa[128 * a + 1]);
-                xb[a] = make_float2(pb[128 * a], pb[128 * a + 1]);
+                const int n0 = 128 * a + 2 * tid;
+                xa[a] = make_float2(n0 < c.take ? pa[128 * a] : 0.f, n0 + 1 < c.take ? pa[128 * a + 1] : 0.f);
+                xb[a] = make_float2(n0 < c.take ? pb[128 * a] : 0.f, n0 + 1 < c.take ? pb[128 * a + 1] : 0.f);
             } else {
                 xa[a] = *reinterpret_cast<const float2 *>(pa + 128 * a);
                 xb[a] = *reinterpret_cast<const float2 *>(pb + 128 * a);
@@ -402,14 +406,16 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
         }
         if (PRE) {
             const bool edgeA = c.firstA && tid == 0, edgeB = c.firstB && tid == 0;
-            pva[0] = *(edgeA ? pa : pa - 1);
-            pvb[0] = *(edgeB ? pb : pb - 1);
+            const bool in0 = !U4 || 2 * tid < c.take;
+            pva[0] = in0 ? *(edgeA ? pa : pa - 1) : 0.f;
+            pvb[0] = in0 ? *(edgeB ? pb : pb - 1) : 0.f;
             if (edgeA) pva[0] = 0.f;
             if (edgeB) pvb[0] = 0.f;
 #pragma unroll
             for (int a = 1; a < R1; a++) {
-                pva[a] = pa[128 * a - 1];
-                pvb[a] = pb[128 * a - 1];
+                const bool in = !U4 || 128 * a + 2 * tid < c.take;          // the sample this one precedes is inside the frame
+                pva[a] = in ? pa[128 * a - 1] : 0.f;
+                pvb[a] = in ? pb[128 * a - 1] : 0.f;
             }
         }
         const W8Trig<(R1 <= 8 ? R1 : 8)> trig(c.tw1[(s * (R1 - 1)) * 32 + lane]);      // unused (and dropped) for R1 = 16
@@ -903,11 +909,12 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     c.cw_lanes = p.tb.cw_lanes;
     c.dct_row = p.tb.dct_row;
     c.lm_part = p.tb.lm_part;
+    c.take = p.take;
     const uint32_t n_warps = gridDim.x * NW;
     for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
         w8_set_item(p, c, item);
         if (!EMB) c.eacc = nullptr;
-        w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8), U4>(c, lane);
+        w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8 && !U4), U4>(c, lane);
         if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
         __syncwarp();
 #if !defined(DSPX_ABL) || DSPX_ABL != 5
@@ -976,7 +983,7 @@ inline int warp8_radix(const dspx_plan *pl) { return pl->P == 512 ? 4 : (pl->P =
 
 inline bool warp8_supported(const dspx_plan *pl)
 {
-    return warp8_radix(pl) != 0 && pl->cfg.frame_length == pl->P &&
+    return warp8_radix(pl) != 0 && pl->cfg.frame_length >= 2 &&
            pl->cfg.n_mels <= 256 && pl->cfg.n_mfcc <= 128 && pl->host.two_band_ok;
 }
 
@@ -1030,8 +1037,9 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         for (int a = 0; a < R1; a++)
             for (int l = 0; l < 32; l++) {
                 const int n = 128 * a + 2 * (l + 32 * s);
-                blob[tb.win + ((s * R1 + a) * 32 + l) * 2] = (float)(0.5 * h.window[n]);
-                blob[tb.win + ((s * R1 + a) * 32 + l) * 2 + 1] = (float)(0.5 * h.window[n + 1]);
+                const int take = std::min(pl->cfg.frame_length, P);          // zero padding / truncation (fft.py:32-36)
+                blob[tb.win + ((s * R1 + a) * 32 + l) * 2] = n < take ? (float)(0.5 * h.window[n]) : 0.f;
+                blob[tb.win + ((s * R1 + a) * 32 + l) * 2 + 1] = n + 1 < take ? (float)(0.5 * h.window[n + 1]) : 0.f;
             }
     for (int s = 0; s < 2; s++)
         for (int ka = 1; ka < R1; ka++)
@@ -1159,7 +1167,7 @@ inline int warp8_prepare(dspx_plan *pl)
     pd->smem_wide = (tb.r1 != 16 && wide + 1024 <= 227 * 1024 && !getenv("DSPX_W8_NARROW")) ? wide : 0;
     const size_t r16 = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_R16);
     pd->smem_r16 = (tb.r1 == 16 && W8_WARPS_R16 > W8_WARPS && r16 + 1024 <= 227 * 1024) ? r16 : 0;
-    pd->share = (2 * pl->cfg.hop_length == pl->P) && !getenv("DSPX_W8_NOSHARE");
+    pd->share = (2 * pl->cfg.hop_length == pl->P) && pl->cfg.frame_length == pl->P && !getenv("DSPX_W8_NOSHARE");
     pl->fast_host = pd;
     DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));
     DSPX_CUDA_CHECK(cudaMemcpy(pl->d_fast_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1252,7 +1260,8 @@ inline bool warp8_can_launch(const float *clips, int64_t n_clips, int64_t clip_s
 // an 8-byte boundary: even hop, even row stride, aligned base
 inline bool warp8_aligned(const dspx_plan *pl, const float *clips, int64_t clip_stride)
 {
-    return !(pl->cfg.hop_length & 1) && !(clip_stride & 1) && !(reinterpret_cast<uintptr_t>(clips) & 7);
+    return pl->cfg.frame_length == pl->P && !(pl->cfg.hop_length & 1) && !(clip_stride & 1) &&
+           !(reinterpret_cast<uintptr_t>(clips) & 7);
 }
 
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
@@ -1277,6 +1286,7 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.n_mels = pl->cfg.n_mels;
     p.n_mfcc = pl->cfg.n_mfcc;
     p.prefetch = 1;
+    p.take = std::min(pl->cfg.frame_length, pl->P);
     p.share = pd->share;
     p.alpha = (float)pl->cfg.pre_emphasis;
     p.win_a = pl->cfg.window == DSPX_WINDOW_HANN ? 0.25f : (pl->cfg.window == DSPX_WINDOW_HAMMING ? 0.27f : 0.5f);
