@@ -79,6 +79,8 @@ _SIGNATURES = {
     "dspx_cmvn": (_I32, [_VP, _I64, _I64, _I32, C.c_double, _VP]),
     "dspx_features_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP]),
     "dspx_pcm16_to_float": (_I32, [_VP, _I64, _I64, _I64, _I32, _VP, _I64, _VP]),
+    "dspx_features_pcm16_workspace": (_SZ, [_I64]),
+    "dspx_features_pcm16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "dspx_features_host_pcm16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP, _VP, _VP]),
     "dspx_stft_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32, _VP]),
     "dspx_next_pow_two": (_I64, [_I64]),

@@ -88,6 +88,34 @@ def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int
         import torch
 
         if _is_pcm16(clips):
+            pcm = clips if clips.dim() == 2 else clips[None, :]
+            pcm = pcm if pcm.stride(1) == 1 else pcm.contiguous()
+            dev = pcm.device.index if device is None else device
+            plan = get_plan(cfg, dev, kernel)
+            if plan.kernel == "warp8":
+                # conversion and peak normalisation inside the feature kernel's loads: no float32 copy of the clips
+                b, length = pcm.shape
+                t = plan.num_frames(length)
+                need_mfcc = "mfcc" in want or "embed" in want
+                with torch.cuda.device(dev):
+                    lm = torch.empty((b, t, plan.n_mels), dtype=torch.float32, device=pcm.device) if "log_mel" in want else None
+                    mf = torch.empty((b, t, plan.n_mfcc), dtype=torch.float32, device=pcm.device) if need_mfcc else None
+                    em = torch.empty((b, 2 * plan.n_mfcc), dtype=torch.float32, device=pcm.device) if "embed" in want else None
+                    ws_bytes = int(lib.dspx_features_pcm16_workspace(b))
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pcm.device)
+                    _lib.check(lib.dspx_features_pcm16(plan.handle, pcm.data_ptr(), b, length, pcm.stride(0), 1 if normalize else 0,
+                                                       lm.data_ptr() if lm is not None else None,
+                                                       mf.data_ptr() if mf is not None else None,
+                                                       em.data_ptr() if em is not None else None, ws.data_ptr(), ws_bytes,
+                                                       torch.cuda.current_stream(dev).cuda_stream), "dspx_features_pcm16")
+                out = {}
+                if lm is not None:
+                    out["log_mel"] = lm
+                if "mfcc" in want:
+                    out["mfcc"] = mf
+                if em is not None:
+                    out["embed"] = em
+                return out
             clips = pcm16_to_float(clips, normalize)
         x = clips if clips.dim() == 2 else clips[None, :]
         if x.dtype != torch.float32 or x.stride(1) != 1:

@@ -220,6 +220,31 @@ static int features_device(const dspx_plan *pl, const float *clips, int64_t n_cl
     return rc;
 }
 
+// PCM16 clips on the device -> features, conversion and peak normalisation inside the feature kernel's sample loads.
+// peaks_ws: n_clips ints of scratch (only touched when normalize).  warp8 plans only.
+static int features_device_pcm16(const dspx_plan *pl, const int16_t *pcm, int64_t n_clips, int64_t clip_len, int64_t pcm_stride,
+                                 int normalize, float *logmel, float *mfcc, float *embed, int *peaks_ws, cudaStream_t st)
+{
+    const int64_t T = dspx_num_frames(pl, clip_len);
+    if (T < 0) return DSPX_EINVAL;
+    if (pl->kernel != DSPX_KERNEL_WARP8) {
+        set_error("fused PCM16 ingest needs the warp8 kernel (n_fft 512 / 1024 / 2048): convert with dspx_pcm16_to_float first");
+        return DSPX_EUNSUPPORTED;
+    }
+    DSPX_REQUIRE(!embed || mfcc, "embed_out needs mfcc_out on the PCM16 path");
+    DSPX_REQUIRE(n_clips < (int64_t)2147483647, "too many clips for one launch");
+    if (normalize) {
+        DSPX_REQUIRE(peaks_ws, "peak normalisation needs the workspace");
+        pcm16_peak_kernel<<<(unsigned)n_clips, 256, 0, st>>>(pcm, clip_len, pcm_stride, peaks_ws);
+        DSPX_CUDA_CHECK(cudaGetLastError());
+    }
+    int rc = launch_warp8(pl, reinterpret_cast<const float *>(pcm), n_clips, clip_len, pcm_stride, T, logmel, mfcc, st, 0,
+                          nullptr, 0, nullptr, 1, normalize ? peaks_ws : nullptr);
+    if (rc != DSPX_OK) return rc;
+    if (embed) rc = launch_embed(mfcc, n_clips, T, pl->cfg.n_mfcc, embed, st);
+    return rc;
+}
+
 // complex STFT: the warp8 kernel when frame_length == n_fft in {512, 1024, 2048} and the rows are aligned
 static int stft_device(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
                        int64_t T, int pre, float2 *out, cudaStream_t st)
@@ -337,8 +362,8 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     const size_t lm_b = (mode == 0 && o_logmel) ? (size_t)T * pl->cfg.n_mels * 4 : 0;
     // embeddings alone: accumulated inside the feature kernel (16 bytes of scratch per coefficient instead of an
     // MFCC tensor); otherwise they are the statistics of the MFCCs that are written anyway
-    const bool fused_embed = mode == 0 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8 && !(clip_len & 1) &&
-                             !(pl->cfg.hop_length & 1);
+    const bool fused_embed = mode == 0 && elem == 4 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8 &&
+                             !(clip_len & 1) && !(pl->cfg.hop_length & 1);
     const bool need_mfcc = mode == 0 && (o_mfcc || (o_embed && !fused_embed));
     const size_t mf_b = need_mfcc ? (size_t)T * pl->cfg.n_mfcc * 4 : (fused_embed ? (size_t)pl->cfg.n_mfcc * 16 : 0);
     const size_t em_b = (mode == 0 && o_embed) ? (size_t)2 * pl->cfg.n_mfcc * 4 : 0;
@@ -360,8 +385,11 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     HostPipe *hp = static_cast<HostPipe *>(pl->host_pipe);
     DSPX_REQUIRE(hp, "plan has no host pipeline state");
     std::lock_guard<std::mutex> lock(hp->mu);
+    // PCM16 on a warp8 plan: the feature kernel converts in its own loads (no float32 copy of the clips); the scratch
+    // buffer then only holds one int per clip.  Other plans convert first (pcm16_to_float_kernel) and need the copy.
+    const bool fused_pcm = elem == 2 && mode == 0 && pl->kernel == DSPX_KERNEL_WARP8;
     int rc = ensure_pipe(pl, clip_bytes * chunk, out_bytes, !in_pinned, !out_pinned, &hp,
-                         elem == 2 ? (size_t)clip_len * 4 * chunk : 0);
+                         elem == 2 ? (fused_pcm ? (size_t)chunk * sizeof(int) : (size_t)clip_len * 4 * chunk) : 0);
     if (rc != DSPX_OK) return rc;
     // "_host" contract: nothing may still be reading the caller's input or writing the caller's output when
     // the call returns, also on the error paths below
@@ -407,7 +435,7 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
             DSPX_CUDA_CHECK(cudaMemcpyAsync(d_raw, h, clip_bytes * cnt, cudaMemcpyHostToDevice, st));
         }
         float *d_clips = static_cast<float *>(d_raw);
-        if (elem == 2) {
+        if (elem == 2 && !fused_pcm) {
             d_clips = static_cast<float *>(hp->d_f32[slot]);
             pcm16_to_float_kernel<<<(unsigned)cnt, 256, 0, st>>>(static_cast<const int16_t *>(d_raw), clip_len, clip_len,
                                                                  normalize, d_clips, clip_len);
@@ -417,7 +445,10 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
         float *d_mf = mf_b ? reinterpret_cast<float *>(d_o + off_mf) : nullptr;
         float *d_em = em_b ? reinterpret_cast<float *>(d_o + off_em) : nullptr;
         float *d_st = st_b ? reinterpret_cast<float *>(d_o + off_st) : nullptr;
-        if (mode == 0)
+        if (fused_pcm)
+            rc = features_device_pcm16(pl, static_cast<const int16_t *>(d_raw), cnt, clip_len, clip_len, normalize, d_lm, d_mf,
+                                       d_em, static_cast<int *>(hp->d_f32[slot]), st);
+        else if (mode == 0)
             rc = fused_embed ? features_device(pl, d_clips, cnt, clip_len, clip_len, d_lm, nullptr, d_em, st, 0,
                                                reinterpret_cast<long long *>(d_mf))
                              : features_device(pl, d_clips, cnt, clip_len, clip_len, d_lm, d_mf, d_em, st);
@@ -713,6 +744,25 @@ int dspx_pcm16_to_float(const int16_t *pcm_dev, int64_t n_clips, int64_t clip_le
                                                                                             normalize ? 1 : 0, out_dev, out_stride);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
+}
+
+size_t dspx_features_pcm16_workspace(int64_t n_clips) { return n_clips > 0 ? (size_t)n_clips * sizeof(int) + 256 : 256; }
+
+int dspx_features_pcm16(const dspx_plan *plan, const int16_t *pcm_dev, int64_t n_clips, int64_t clip_len, int64_t pcm_stride,
+                        int normalize, float *logmel_out_dev, float *mfcc_out_dev, float *embed_out_dev, void *workspace_dev,
+                        size_t workspace_bytes, void *stream)
+{
+    DSPX_REQUIRE(plan && pcm_dev, "null argument");
+    DSPX_REQUIRE(n_clips >= 0 && clip_len > 0 && pcm_stride >= clip_len, "bad clip buffer arguments");
+    DSPX_REQUIRE(logmel_out_dev || mfcc_out_dev, "no output requested");
+    DSPX_REQUIRE(!normalize || (workspace_dev && workspace_bytes >= dspx_features_pcm16_workspace(n_clips)), "workspace too small");
+    if (dspx_num_frames(plan, clip_len) < 0) return DSPX_EINVAL;
+    if (n_clips == 0) return DSPX_OK;
+    DeviceGuard guard(plan->device);
+    char *ws = static_cast<char *>(workspace_dev);
+    if (ws) ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
+    return features_device_pcm16(plan, pcm_dev, n_clips, clip_len, pcm_stride, normalize ? 1 : 0, logmel_out_dev, mfcc_out_dev,
+                                 embed_out_dev, reinterpret_cast<int *>(ws), static_cast<cudaStream_t>(stream));
 }
 
 int dspx_features_host_pcm16(const dspx_plan *plan, const int16_t *pcm_host, int64_t n_clips, int64_t clip_len,

@@ -255,4 +255,24 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     return DSPX_OK;
 }
 
+// Exhaustive check of the fused PCM16 normalisation (w8_pcm_to_float): for every peak m in [1, 32768] and every sample
+// |s| <= m, the value the feature kernel feeds to the transform must equal NumPy's float32 (s / 32768) / (m / 32768).
+// Returns the number of mismatches (0 expected) and the number of pairs through *total.
+long long emu_pcm16_quotient_mismatches(long long *total)
+{
+    long long bad = 0, n = 0;
+#pragma omp parallel for reduction(+ : bad, n) schedule(dynamic, 64)
+    for (int m = 1; m <= 32768; m++) {
+        const float fm = (float)m, r = 1.0f / fm, peak = fm * (1.0f / 32768.0f);
+        for (int s = -m; s <= m; s++) {
+            if (s > 32767) continue;
+            const float ref = ((float)s * (1.0f / 32768.0f)) / peak;
+            if (dspx::w8_pcm_to_float(s, fm, r) != ref) bad++;
+            n++;
+        }
+    }
+    if (total) *total = n;
+    return bad;
+}
+
 }  // extern "C"

@@ -208,6 +208,7 @@ struct W8Params {
     int64_t lm_ts, lm_fs;    // log-mel strides between frames / filters ([B,T,M]: M,1; [B,1,M,T]: 1,T)
     float2 *stft;            // STFT mode: complex spectrum [n_clips, n_frames, M + 1]
     long long *eacc;         // embedding accumulators [n_clips][2][n_mfcc] (fixed point, see w8_embed_accumulate) or null
+    const int *peaks;        // PCM variant: max |sample| of every clip (peak normalisation), null = divide by 32768 only
 };
 
 struct W8Ctx {               // everything one warp needs for one frame pair
@@ -229,6 +230,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     int64_t lm_fs;
     float2 *stftA, *stftB;   // STFT mode: rows of the two frames
     long long *eacc;         // this clip's embedding accumulators: sum x [n_mfcc], sum x^2 [n_mfcc]
+    float pcm_m, pcm_r;      // PCM variant: the clip's max |sample| m (0 = no normalisation) and 1 / m
 };
 
 struct W8Power {             // |X|^2 of the bins one pass-3 unit owns, carried across the syncwarp
@@ -316,6 +318,30 @@ template <int R1, bool TRIG, class Trig> DSPX_HD float2 w8_twiddle_of(const W8Ct
     return c.tw1[(s * (R1 - 1) + ka - 1) * 32 + lane];
 }
 
+// ---- PCM16 ingest inside the sample loads (general variant only) ---------------------------
+// load_audio + normalize_audio (src/utils/audio.py:19-38) of a 16-bit PCM clip are x = s / 32768 and x / max|x|,
+// i.e. the correctly rounded quotient s / m with m = max|s| (both scalings are exact).  q = s * (1/m) followed by one
+// fma refinement, q' = q + (s - m q) / m, IS that quotient for every |s| <= m <= 32768: verified exhaustively
+// (1 073 807 359 pairs, tests/test_host_and_abi.py::test_pcm16_quotient_is_exact), so the fused path feeds the
+// transform bit-for-bit the samples dspx_pcm16_to_float writes -- without the float32 copy of the clips in HBM.
+DSPX_HD float w8_pcm_to_float(int s, float m, float r)
+{
+    const float x = (float)s;
+    if (m == 0.f) return x * (1.0f / 32768.0f);               // no normalisation, or an all-zero clip
+    const float q = x * r;
+    return fmaf(fmaf(-m, q, x), r, q);
+}
+
+template <bool PCM> struct W8Sample { using type = float; };
+template <> struct W8Sample<true> { using type = int16_t; };
+
+template <bool PCM>
+DSPX_HD float w8_fetch(const typename W8Sample<PCM>::type *p, const W8Ctx &c)
+{
+    if (PCM) return w8_pcm_to_float((int)*p, c.pcm_m, c.pcm_r);
+    return (float)*p;
+}
+
 // ---- phase A: load, pre-emphasis, window, radix-R1 over a, twiddle, store -----------------
 // All loads of a set are issued before the first use (memory-level parallelism); the only
 // sample without a predecessor is sample 0 of a clip (y[0] = x[0], src/dsp/mfcc.py:88).
@@ -325,9 +351,10 @@ template <int R1, bool TRIG, class Trig> DSPX_HD float2 w8_twiddle_of(const W8Ct
 // may be shorter than the transform (frame_length < n_fft: zero padding, src/dsp/fft.py:34-36) or longer (truncation,
 // fft.py:32-33).  The two samples of a lane are fetched with two 4-byte loads, each only if it lies inside the
 // first c.take samples of the frame; the window comes from the table (zero past take).  Never combined with SHARE.
-template <int R1, bool PRE, bool SHARE, bool TRIG, bool U4 = false>
+template <int R1, bool PRE, bool SHARE, bool TRIG, bool U4 = false, bool PCM = false>
 DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 {
+    static_assert(!PCM || (U4 && !SHARE), "the PCM16 loads exist in the general variant only");
     if (SHARE) {
         // hop == n_fft / 2: frame B's rows 0..R1/2-1 are frame A's rows R1/2..R1-1.  Load the 3/2 R1
         // distinct rows once, pre-emphasise them once (scalar), and pair them up for the two frames.
@@ -390,15 +417,16 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         const int tid = lane + 32 * s;
-        const float *pa = c.fa + 2 * tid, *pb = c.fb + 2 * tid;
+        using S = typename W8Sample<PCM>::type;                               // float, or int16 (c.fa / c.fb then point at int16)
+        const S *pa = reinterpret_cast<const S *>(c.fa) + 2 * tid, *pb = reinterpret_cast<const S *>(c.fb) + 2 * tid;
         float2 xa[R1], xb[R1];
         float pva[R1], pvb[R1];
 #pragma unroll
         for (int a = 0; a < R1; a++) {
             if (U4) {
                 const int n0 = 128 * a + 2 * tid;
-                xa[a] = make_float2(n0 < c.take ? pa[128 * a] : 0.f, n0 + 1 < c.take ? pa[128 * a + 1] : 0.f);
-                xb[a] = make_float2(n0 < c.take ? pb[128 * a] : 0.f, n0 + 1 < c.take ? pb[128 * a + 1] : 0.f);
+                xa[a] = make_float2(n0 < c.take ? w8_fetch<PCM>(pa + 128 * a, c) : 0.f, n0 + 1 < c.take ? w8_fetch<PCM>(pa + 128 * a + 1, c) : 0.f);
+                xb[a] = make_float2(n0 < c.take ? w8_fetch<PCM>(pb + 128 * a, c) : 0.f, n0 + 1 < c.take ? w8_fetch<PCM>(pb + 128 * a + 1, c) : 0.f);
             } else {
                 xa[a] = *reinterpret_cast<const float2 *>(pa + 128 * a);
                 xb[a] = *reinterpret_cast<const float2 *>(pb + 128 * a);
@@ -407,15 +435,15 @@ DSPX_HD void w8_pass1(const W8Ctx &c, int lane)
         if (PRE) {
             const bool edgeA = c.firstA && tid == 0, edgeB = c.firstB && tid == 0;
             const bool in0 = !U4 || 2 * tid < c.take;
-            pva[0] = in0 ? *(edgeA ? pa : pa - 1) : 0.f;
-            pvb[0] = in0 ? *(edgeB ? pb : pb - 1) : 0.f;
+            pva[0] = in0 ? w8_fetch<PCM>(edgeA ? pa : pa - 1, c) : 0.f;
+            pvb[0] = in0 ? w8_fetch<PCM>(edgeB ? pb : pb - 1, c) : 0.f;
             if (edgeA) pva[0] = 0.f;
             if (edgeB) pvb[0] = 0.f;
 #pragma unroll
             for (int a = 1; a < R1; a++) {
                 const bool in = !U4 || 128 * a + 2 * tid < c.take;          // the sample this one precedes is inside the frame
-                pva[a] = in ? pa[128 * a - 1] : 0.f;
-                pvb[a] = in ? pb[128 * a - 1] : 0.f;
+                pva[a] = in ? w8_fetch<PCM>(pa + 128 * a - 1, c) : 0.f;
+                pvb[a] = in ? w8_fetch<PCM>(pb + 128 * a - 1, c) : 0.f;
             }
         }
         const W8Trig<(R1 <= 8 ? R1 : 8)> trig(c.tw1[(s * (R1 - 1)) * 32 + lane]);      // unused (and dropped) for R1 = 16
@@ -844,14 +872,21 @@ __global__ void embed_finalize_kernel(const long long *eacc, int64_t n_clips, in
 #endif
 
 // set the per-item fields of the context (item = clip * pairs_per_clip + pair)
+template <bool PCM = false>
 DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
 {
     const uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
     const int64_t tA = 2 * (int64_t)pair, tB = tA + 1;
     c.validB = tB < p.n_frames;
-    const float *base = p.clips + (int64_t)clip * p.clip_stride;
-    c.fa = base + tA * p.hop;
-    c.fb = c.validB ? base + tB * p.hop : c.fa;
+    using S = typename W8Sample<PCM>::type;                  // strides and hops count samples of the clip's own type
+    const S *base = reinterpret_cast<const S *>(p.clips) + (int64_t)clip * p.clip_stride;
+    c.fa = reinterpret_cast<const float *>(base + tA * p.hop);
+    c.fb = c.validB ? reinterpret_cast<const float *>(base + tB * p.hop) : c.fa;
+    if (PCM) {
+        const int m = p.peaks ? p.peaks[clip] : 0;
+        c.pcm_m = (float)m;
+        c.pcm_r = m > 0 ? 1.0f / (float)m : 0.f;              // IEEE division: the correctly rounded reciprocal
+    }
     c.firstA = pair == 0;
     c.firstB = c.validB ? 0 : c.firstA;        // a missing frame B replays frame A
     const int64_t rowA = (int64_t)clip * p.n_frames + tA, rowB = rowA + 1;
@@ -869,19 +904,19 @@ DSPX_HD void w8_set_item(const W8Params &p, W8Ctx &c, uint32_t item)
 // the whole per-item sequence; SYNC is __syncwarp() on the device and a no-op in the lane-loop replay
 #if defined(__CUDACC__)
 // pull the next item's samples towards L2 while this one is being transformed
-__device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, int lane, int n_fft)
+__device__ __forceinline__ void w8_prefetch(const W8Params &p, uint32_t item, int lane, int n_fft, int elem = 4)
 {
     if (item >= p.n_items) return;
     const uint32_t clip = item / p.pairs_per_clip, pair = item - clip * p.pairs_per_clip;
-    const char *base = reinterpret_cast<const char *>(p.clips + (int64_t)clip * p.clip_stride + 2 * (int64_t)pair * p.hop);
-    const int span = (p.hop + n_fft) * 4;                      // bytes covered by the frame pair
+    const char *base = reinterpret_cast<const char *>(p.clips) + ((int64_t)clip * p.clip_stride + 2 * (int64_t)pair * p.hop) * elem;
+    const int span = (p.hop + n_fft) * elem;                   // bytes covered by the frame pair
     for (int off = lane * 128; off < span; off += 32 * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
 // EMB: accumulate clip embeddings (w8_embed_accumulate); a template switch so that the plain feature kernels keep
 // their register allocation (the extra pointer alone pushed the 96-register headline variant into spills)
-template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false, bool U4 = false>
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false, bool U4 = false, bool PCM = false>
 __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_warp8_kernel(const W8Params p)
 {
     using G = W8Geo<R1>;
@@ -912,10 +947,10 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
     c.take = p.take;
     const uint32_t n_warps = gridDim.x * NW;
     for (uint32_t item = blockIdx.x * NW + warp; item < p.n_items; item += n_warps) {
-        w8_set_item(p, c, item);
+        w8_set_item<PCM>(p, c, item);
         if (!EMB) c.eacc = nullptr;
-        w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8 && !U4), U4>(c, lane);
-        if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P);
+        w8_pass1<R1, PRE, SHARE, (!STFT && R1 <= 8 && !U4), U4, PCM>(c, lane);
+        if (p.prefetch) w8_prefetch(p, item + n_warps, lane, G::P, PCM ? 2 : 4);
         __syncwarp();
 #if !defined(DSPX_ABL) || DSPX_ABL != 5
         w8_pass2<R1>(c, lane);
@@ -1184,12 +1219,12 @@ inline void warp8_release(dspx_plan *pl)
 int launch_generic_fallback(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                             int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw);
 
-template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false, bool U4 = false>
+template <int R1, bool PRE, bool STFT, bool SHARE, int NW, bool EMB = false, bool U4 = false, bool PCM = false>
 inline int w8_launch_nw(const W8Params &p, size_t smem, int device, int64_t ctas, cudaStream_t st)
 {
     static std::atomic<unsigned char> optin[64];
-    DSPX_CUDA_CHECK(optin_max_smem(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB, U4>, optin, device));
-    feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB, U4><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
+    DSPX_CUDA_CHECK(optin_max_smem(feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB, U4, PCM>, optin, device));
+    feat_warp8_kernel<R1, PRE, STFT, SHARE, NW, EMB, U4, PCM><<<(unsigned)ctas, NW * 32, smem, st>>>(p);
     DSPX_CUDA_CHECK(cudaGetLastError());
     return DSPX_OK;
 }
@@ -1220,23 +1255,23 @@ inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, in
 }
 
 // features from frames that are not 8-byte aligned: 4-byte sample loads, no row sharing, no fused embeddings
-template <int R1, bool PRE>
+template <int R1, bool PRE, bool PCM = false>
 inline int w8_launch_u4(const W8Params &p, const W8PlanData *pd, int device, int sm_count, cudaStream_t st)
 {
     if (R1 != 16 && pd->smem_wide) {
         int64_t ctas = ((int64_t)p.n_items + W8_WARPS_WIDE - 1) / W8_WARPS_WIDE;
         if (ctas > sm_count) ctas = sm_count;
-        return w8_launch_nw<R1, PRE, false, false, (R1 != 16) ? W8_WARPS_WIDE : W8_WARPS, false, true>(p, pd->smem_wide, device, ctas, st);
+        return w8_launch_nw<R1, PRE, false, false, (R1 != 16) ? W8_WARPS_WIDE : W8_WARPS, false, true, PCM>(p, pd->smem_wide, device, ctas, st);
     }
     if (R1 == 16 && pd->smem_r16) {
         int64_t ctas = ((int64_t)p.n_items + W8_WARPS_R16 - 1) / W8_WARPS_R16;
         if (ctas > sm_count) ctas = sm_count;
-        return w8_launch_nw<R1, PRE, false, false, (R1 == 16) ? W8_WARPS_R16 : W8_WARPS, false, true>(p, pd->smem_r16, device, ctas, st);
+        return w8_launch_nw<R1, PRE, false, false, (R1 == 16) ? W8_WARPS_R16 : W8_WARPS, false, true, PCM>(p, pd->smem_r16, device, ctas, st);
     }
     int64_t ctas = ((int64_t)p.n_items + W8_WARPS - 1) / W8_WARPS;
     const int64_t resident = (int64_t)sm_count * pd->ctas_per_sm;
     if (ctas > resident) ctas = resident;
-    return w8_launch_nw<R1, PRE, false, false, W8_WARPS, false, true>(p, pd->smem, device, ctas, st);
+    return w8_launch_nw<R1, PRE, false, false, W8_WARPS, false, true, PCM>(p, pd->smem, device, ctas, st);
 }
 
 template <int R1, bool PRE, bool STFT>
@@ -1266,10 +1301,16 @@ inline bool warp8_aligned(const dspx_plan *pl, const float *clips, int64_t clip_
 
 inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len,
                         int64_t clip_stride, int64_t T, float *logmel, float *mfcc, cudaStream_t st, int nchw = 0,
-                        float2 *stft = nullptr, int stft_pre = 0, long long *eacc = nullptr)
+                        float2 *stft = nullptr, int stft_pre = 0, long long *eacc = nullptr, int pcm = 0,
+                        const int *peaks = nullptr)
 {
     const int64_t pairs = (T + 1) / 2;
-    const bool aligned = warp8_aligned(pl, clips, clip_stride);
+    // pcm: `clips` points at int16 samples (strides in samples); always the general variant
+    const bool aligned = !pcm && warp8_aligned(pl, clips, clip_stride);
+    if (pcm && (stft || eacc || !warp8_can_launch(clips, n_clips, clip_stride, T))) {
+        set_error("warp8 pcm16 ingest: features only, at most 2^31 frame pairs per launch");
+        return DSPX_EUNSUPPORTED;
+    }
     if (!warp8_can_launch(clips, n_clips, clip_stride, T) || (!aligned && (stft || eacc))) {
         if (stft || eacc) { set_error("warp8 stft / fused embeddings: unaligned clips or batch too large"); return DSPX_EUNSUPPORTED; }
         return launch_generic_fallback(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
@@ -1299,6 +1340,7 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
     p.lm_fs = nchw ? T : 1;
     p.stft = stft;
     p.eacc = eacc;
+    p.peaks = peaks;
     const int ctas = pl->sm_count;                           // grid size is derived per configuration in w8_launch_cfg
 #ifdef DSPX_W8_LAB
     // benchmarks/lab/w8_lab.cu: only the headline instantiation, for quick builds of kernel variants
@@ -1313,6 +1355,13 @@ inline int launch_warp8(const dspx_plan *pl, const float *clips, int64_t n_clips
         }
     }
     const bool pre = pl->cfg.pre_emphasis > 0.0;
+    if (pcm) {
+        switch (pd->tb.r1) {
+            case 4: return pre ? w8_launch_u4<4, true, true>(p, pd, pl->device, ctas, st) : w8_launch_u4<4, false, true>(p, pd, pl->device, ctas, st);
+            case 8: return pre ? w8_launch_u4<8, true, true>(p, pd, pl->device, ctas, st) : w8_launch_u4<8, false, true>(p, pd, pl->device, ctas, st);
+            case 16: return pre ? w8_launch_u4<16, true, true>(p, pd, pl->device, ctas, st) : w8_launch_u4<16, false, true>(p, pd, pl->device, ctas, st);
+        }
+    }
     if (!aligned) {
         switch (pd->tb.r1) {
             case 4: return pre ? w8_launch_u4<4, true>(p, pd, pl->device, ctas, st) : w8_launch_u4<4, false>(p, pd, pl->device, ctas, st);

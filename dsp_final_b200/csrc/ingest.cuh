@@ -41,6 +41,34 @@ __global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t *pcm,
         dst[i] = normalize ? __fdiv_rn(x, peak) : x;
     }
 }
+// max |sample| of every clip: all the fused PCM16 path needs before the feature kernel converts the samples in its
+// own loads (w8_pcm_to_float).  One CTA per clip; the clip was just copied to the device, so this read is L2-warm.
+__global__ void __launch_bounds__(256) pcm16_peak_kernel(const int16_t *pcm, int64_t clip_len, int64_t pcm_stride, int *peaks)
+{
+    const int16_t *src = pcm + (size_t)blockIdx.x * pcm_stride;
+    __shared__ int s_peak[8];
+    int m = 0;
+    const int64_t pairs = ((reinterpret_cast<uintptr_t>(src) & 3) == 0) ? clip_len / 2 : 0;      // 32-bit loads when aligned
+    const int *src2 = reinterpret_cast<const int *>(src);
+    for (int64_t i = threadIdx.x; i < pairs; i += 256) {
+        const int v = src2[i];
+        const int lo = (int)(short)(v & 0xffff), hi = v >> 16;
+        m = max(m, max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi));
+    }
+    for (int64_t i = 2 * pairs + threadIdx.x; i < clip_len; i += 256) {
+        const int v = src[i];
+        m = max(m, v < 0 ? -v : v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) s_peak[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; w++) m = max(m, s_peak[w]);
+        peaks[blockIdx.x] = m;
+    }
+}
 #endif
 
 }  // namespace dspx

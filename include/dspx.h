@@ -160,6 +160,14 @@ int dspx_stft_host(const dspx_plan *plan, const float *clips_host, int64_t n_cli
  * to NumPy.  The _host form ships int16 over PCIe (half the bytes of float32 clips). */
 int dspx_pcm16_to_float(const int16_t *pcm_dev, int64_t n_clips, int64_t clip_len, int64_t pcm_stride,
                         int normalize, float *out_dev, int64_t out_stride, void *stream);
+/* Device-pointer form with the conversion FUSED into the feature kernel's sample loads (warp8 plans: n_fft 512 / 1024 /
+ * 2048; DSPX_EUNSUPPORTED otherwise): no float32 copy of the clips exists.  q = s * (1/m), one fma refinement -- the
+ * correctly rounded s / m for every |s| <= m <= 32768 (checked exhaustively), i.e. the same samples as above.
+ * workspace_dev (dspx_features_pcm16_workspace bytes) holds one peak per clip; unused when normalize == 0. */
+size_t dspx_features_pcm16_workspace(int64_t n_clips);
+int dspx_features_pcm16(const dspx_plan *plan, const int16_t *pcm_dev, int64_t n_clips, int64_t clip_len,
+                        int64_t pcm_stride, int normalize, float *logmel_out_dev, float *mfcc_out_dev,
+                        float *embed_out_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 int dspx_features_host_pcm16(const dspx_plan *plan, const int16_t *pcm_host, int64_t n_clips,
                              int64_t clip_len, int64_t pcm_stride, int normalize,
                              float *logmel_out_host, float *mfcc_out_host, float *embed_out_host);

@@ -172,6 +172,16 @@ def test_warp8_kernel_replay_matches_reference(built, golden_small):
     assert covered >= 18
 
 
+def test_pcm16_quotient_is_exact(built):
+    """The PCM16 conversion fused into the feature kernel's loads -- q = s (1/m), one fma refinement -- is the
+    correctly rounded (s / 32768) / (m / 32768) of load_audio + normalize_audio for EVERY sample / peak pair."""
+    lib, _ = _emu(built)
+    lib.emu_pcm16_quotient_mismatches.restype = C.c_longlong
+    total = C.c_longlong(0)
+    assert lib.emu_pcm16_quotient_mismatches(C.byref(total)) == 0
+    assert total.value == sum(min(2 * m + 1, m + 32768) for m in range(1, 32769))
+
+
 def test_warp8_replay_unaligned_frames(built):
     """Odd hops and odd row strides put frames off the 8-byte grid: the 4-byte-load variant of the warp8 kernel
     (U4) against the oracle, n_fft 512 / 1024 / 2048 (hop 441 = 10 ms at 44.1 kHz is a common setting)."""

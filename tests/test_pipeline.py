@@ -174,7 +174,9 @@ def test_reference_named_pipeline_on_gpu(golden_pipeline, tmp_path):
     dec = {it.filename: (pcm[i].astype(np.float32) / np.float32(32768.0)) for i, it in enumerate(meta.items)}
     dec = {k: v / np.max(np.abs(v)) for k, v in dec.items()}
     emb_l = R.compute_embeddings(meta.items, cfg, loader=lambda it: dec[it.filename])
-    assert np.array_equal(emb_l, emb_r)                                                        # PCM16 ingest is bit-identical
+    # files go through the fused PCM16 loads (general kernel variant), pre-decoded float32 through the aligned variant:
+    # same samples bit for bit (tests/test_gpu_parity.py::test_pcm16_ingest...), float32 round-off apart in the features
+    assert rel_err(emb_l, emb_r) < 1e-6
 
     # --- run_mfcc_retrieval without a cache ---
     res2 = run_mfcc_retrieval(meta, cfg, k_list=k_list)
