@@ -92,7 +92,7 @@ def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int
             pcm = pcm if pcm.stride(1) == 1 else pcm.contiguous()
             dev = pcm.device.index if device is None else device
             plan = get_plan(cfg, dev, kernel)
-            if plan.kernel == "warp8":
+            if plan.kernel == "warp8" and plan.n_fft != 4096:
                 # conversion and peak normalisation inside the feature kernel's loads: no float32 copy of the clips
                 b, length = pcm.shape
                 t = plan.num_frames(length)
@@ -125,7 +125,7 @@ def features_batch(clips, cfg: Any, want: Iterable[str] = ("mfcc",), device: int
         b, length = x.shape
         t = plan.num_frames(length)
         # embeddings without MFCCs: accumulated inside the feature kernel (no [B, T, n_mfcc] tensor at all)
-        fused = ("embed" in want and "mfcc" not in want and plan.kernel == "warp8"
+        fused = ("embed" in want and "mfcc" not in want and plan.kernel == "warp8" and plan.n_fft != 4096
                  and x.data_ptr() % 8 == 0 and x.stride(0) % 2 == 0 and plan.hop_length % 2 == 0)
         need_mfcc = "mfcc" in want or ("embed" in want and not fused)
         with torch.cuda.device(dev):

@@ -12,6 +12,7 @@
 #include "tables.cuh"
 #include "feat_generic.cuh"
 #include "feat_warp8.cuh"
+#include "feat_warp8_x2.cuh"
 #include "fft_generic.cuh"
 #include "retrieval.cuh"
 #include "retrieval_f32.cuh"
@@ -196,7 +197,7 @@ static int features_device(const dspx_plan *pl, const float *clips, int64_t n_cl
     if (T < 0) return DSPX_EINVAL;
     int rc;
     if (embed && !mfcc) {
-        if (!eacc || pl->kernel != DSPX_KERNEL_WARP8 || !warp8_can_launch(clips, n_clips, clip_stride, T) ||
+        if (!eacc || pl->kernel != DSPX_KERNEL_WARP8 || warp8_x2(pl) || !warp8_can_launch(clips, n_clips, clip_stride, T) ||
             !warp8_aligned(pl, clips, clip_stride)) {
             set_error("embeddings without an MFCC buffer need the warp8 kernel and 8-byte aligned clips with an even stride");
             return DSPX_EUNSUPPORTED;
@@ -210,7 +211,9 @@ static int features_device(const dspx_plan *pl, const float *clips, int64_t n_cl
         DSPX_CUDA_CHECK(cudaGetLastError());
         return DSPX_OK;
     }
-    if (pl->kernel == DSPX_KERNEL_WARP8)
+    if (pl->kernel == DSPX_KERNEL_WARP8 && warp8_x2(pl))
+        rc = launch_warp8_x2(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
+    else if (pl->kernel == DSPX_KERNEL_WARP8)
         rc = launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, logmel, mfcc, st, nchw);
     else
         rc = launch_generic(pl, clips, n_clips, clip_len, clip_stride, T, pl->take_feat,
@@ -227,7 +230,7 @@ static int features_device_pcm16(const dspx_plan *pl, const int16_t *pcm, int64_
 {
     const int64_t T = dspx_num_frames(pl, clip_len);
     if (T < 0) return DSPX_EINVAL;
-    if (pl->kernel != DSPX_KERNEL_WARP8) {
+    if (pl->kernel != DSPX_KERNEL_WARP8 || warp8_x2(pl)) {
         set_error("fused PCM16 ingest needs the warp8 kernel (n_fft 512 / 1024 / 2048): convert with dspx_pcm16_to_float first");
         return DSPX_EUNSUPPORTED;
     }
@@ -249,8 +252,8 @@ static int features_device_pcm16(const dspx_plan *pl, const int16_t *pcm, int64_
 static int stft_device(const dspx_plan *pl, const float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
                        int64_t T, int pre, float2 *out, cudaStream_t st)
 {
-    if (pl->kernel == DSPX_KERNEL_WARP8 && pl->take_stft == pl->P && warp8_can_launch(clips, n_clips, clip_stride, T) &&
-        warp8_aligned(pl, clips, clip_stride))
+    if (pl->kernel == DSPX_KERNEL_WARP8 && !warp8_x2(pl) && pl->take_stft == pl->P &&
+        warp8_can_launch(clips, n_clips, clip_stride, T) && warp8_aligned(pl, clips, clip_stride))
         return launch_warp8(pl, clips, n_clips, clip_len, clip_stride, T, nullptr, nullptr, st, 0, out, pre);
     return launch_generic(pl, clips, n_clips, clip_len, clip_stride, T, pl->take_stft, pre, nullptr, nullptr, out, st);
 }
@@ -362,7 +365,7 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     const size_t lm_b = (mode == 0 && o_logmel) ? (size_t)T * pl->cfg.n_mels * 4 : 0;
     // embeddings alone: accumulated inside the feature kernel (16 bytes of scratch per coefficient instead of an
     // MFCC tensor); otherwise they are the statistics of the MFCCs that are written anyway
-    const bool fused_embed = mode == 0 && elem == 4 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8 &&
+    const bool fused_embed = mode == 0 && elem == 4 && o_embed && !o_mfcc && pl->kernel == DSPX_KERNEL_WARP8 && !warp8_x2(pl) &&
                              !(clip_len & 1) && !(pl->cfg.hop_length & 1);
     const bool need_mfcc = mode == 0 && (o_mfcc || (o_embed && !fused_embed));
     const size_t mf_b = need_mfcc ? (size_t)T * pl->cfg.n_mfcc * 4 : (fused_embed ? (size_t)pl->cfg.n_mfcc * 16 : 0);
@@ -387,7 +390,7 @@ static int host_pipeline(dspx_plan *pl, int mode, const void *clips_v, int64_t n
     std::lock_guard<std::mutex> lock(hp->mu);
     // PCM16 on a warp8 plan: the feature kernel converts in its own loads (no float32 copy of the clips); the scratch
     // buffer then only holds one int per clip.  Other plans convert first (pcm16_to_float_kernel) and need the copy.
-    const bool fused_pcm = elem == 2 && mode == 0 && pl->kernel == DSPX_KERNEL_WARP8;
+    const bool fused_pcm = elem == 2 && mode == 0 && pl->kernel == DSPX_KERNEL_WARP8 && !warp8_x2(pl);
     int rc = ensure_pipe(pl, clip_bytes * chunk, out_bytes, !in_pinned, !out_pinned, &hp,
                          elem == 2 ? (fused_pcm ? (size_t)chunk * sizeof(int) : (size_t)clip_len * 4 * chunk) : 0);
     if (rc != DSPX_OK) return rc;

@@ -13,6 +13,7 @@
 #include "tables.cuh"
 #include "feat_generic.cuh"
 #include "feat_warp8.cuh"
+#include "feat_warp8_x2.cuh"
 
 namespace dspx {
 void set_error(const char *, ...) {}
@@ -198,6 +199,40 @@ int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_cli
     c.take = cfg->frame_length < e.P ? cfg->frame_length : e.P;
     const int r1 = tb.r1;
     const int units = r1 >= 8 ? r1 / 8 : 1;
+    if (tb.x2) {
+        // n_fft 4096 (feat_warp8_x2.cuh): one frame per item, the same phase order as feat_warp8_x2_kernel
+        if (stft_out) return DSPX_EUNSUPPORTED;
+        p.pairs_per_clip = (uint32_t)T;
+        p.n_items = (uint32_t)(n_clips * T);
+        const bool al4 = cfg->frame_length >= e.P && !(cfg->hop_length & 3) && !(clip_stride & 3) && !(reinterpret_cast<uintptr_t>(clips) & 15);
+        std::vector<W8Power4> pw4(32 * 2);
+        for (uint32_t item = 0; item < p.n_items; item++) {
+            w8x2_set_item(p, c, item);
+            for (int lane = 0; lane < 32; lane++) {
+                if (pre) { if (al4) w8x2_pass1<true, true>(c, lane); else w8x2_pass1<true, false>(c, lane); }
+                else { if (al4) w8x2_pass1<false, true>(c, lane); else w8x2_pass1<false, false>(c, lane); }
+            }
+            for (int lane = 0; lane < 32; lane++) w8_pass2<16>(c, lane);
+            for (int lane = 0; lane < 32; lane++)
+                for (int w = 0; w < 2; w++) w8x2_pass3(c, lane, w, pw4[lane * 2 + w]);
+            for (int lane = 0; lane < 32; lane++)
+                for (int w = 0; w < 2; w++) w8x2_store_power(c, lane, w, pw4[lane * 2 + w]);
+            for (int lane = 0; lane < 32; lane++) w8x2_mel_chunks(c, lane);
+            for (int lane = 0; lane < 32; lane++) w8_logmel(c, lane);
+            if (c.mfccA) {
+                for (int c0 = 0; c0 < c.n_mfcc; c0 += c.cw_lanes) {
+                    float2 acc[32];
+                    for (int lane = 0; lane < 32; lane++) acc[lane] = w8_dct_partial(c, lane, c0);
+                    for (int lane = 0; lane < 32; lane++) {
+                        float2 t = acc[lane];
+                        if (c.cw_lanes == 16) { t.x += acc[lane ^ 16].x; t.y += acc[lane ^ 16].y; }
+                        w8_dct_store(c, lane, c0, t);
+                    }
+                }
+            }
+        }
+        return DSPX_OK;
+    }
     std::vector<W8Power> pw(32 * 2);
     // the device kernel computes window / twiddles on the feature path and loads them in STFT mode: replay the same
 #define W8_P1(R, PRE_, SH_) do { if (p.stft) w8_pass1<R, PRE_, SH_, false>(c, lane); else if (u4) w8_pass1<R, PRE_, false, false, true>(c, lane); else w8_pass1<R, PRE_, SH_, true>(c, lane); } while (0)

@@ -193,6 +193,8 @@ struct W8Tables {            // offsets (in floats) into the packed table blob /
     int lm_part;             // log-mel row: float2 slots per part (filters f = part, part + parts, ... ; multiple of 2)
     int tile_floats;         // per-warp exchange / power tile
     int r1;                  // first-pass radix (4, 8, 16)
+    int x2;                  // n_fft 4096 (feat_warp8_x2.cuh): one frame per item, its even / odd samples in the (A, B) halves
+    int win4, ptw2, ppos4;   // x2 tables: window per float4 of samples, exp(-2 pi i k / 4096), four tile positions per slot
 };
 
 struct W8Params {
@@ -214,6 +216,9 @@ struct W8Params {
 struct W8Ctx {               // everything one warp needs for one frame pair
     const float2 *win, *tw1, *tw2, *ptw;
     const int2 *ppos;
+    const float4 *win4;      // x2 tables (n_fft 4096)
+    const float2 *ptw2;
+    const int4 *ppos4;
     const float *cw;
     const int *cflag;
     const int4 *fdesc;
@@ -253,13 +258,17 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
     c.tw2 = reinterpret_cast<const float2 *>(tables_smem + tb.tw2);
     c.ptw = reinterpret_cast<const float2 *>(tables_smem + tb.ptw);
     c.ppos = reinterpret_cast<const int2 *>(tables_smem + tb.ppos);
+    c.win4 = reinterpret_cast<const float4 *>(tables_smem + tb.win4);
+    c.ptw2 = reinterpret_cast<const float2 *>(tables_smem + tb.ptw2);
+    c.ppos4 = reinterpret_cast<const int4 *>(tables_smem + tb.ppos4);
     c.cw = tables_smem + tb.cw;
     c.cflag = reinterpret_cast<const int *>(tables_smem + tb.cflag);
     c.fdesc = reinterpret_cast<const int4 *>(tables_smem + tb.fdesc);
     c.dct = tables_smem + tb.dct;
     c.xbuf = reinterpret_cast<float4 *>(warp_smem);
     c.pbuf = reinterpret_cast<float2 *>(warp_smem);
-    c.seg = c.pbuf + (W8_CSTRIDE * tb.n_slots + 16);          // 2 n_segs sums in filter order + one dump slot
+    // power tile: float2 (frame A, frame B) per bin, or one float per bin in the x2 (single frame) mode
+    c.seg = c.pbuf + (tb.x2 ? (W8_CSTRIDE * tb.n_slots + 16) / 2 : (W8_CSTRIDE * tb.n_slots + 16));
     c.lm = c.seg + tb.seg_slots;                             // seg_slots is even: 16-byte aligned for the DCT's 128-bit loads
     c.dsc = c.lm + (32 / tb.cw_lanes) * tb.lm_part;
 }
@@ -1014,7 +1023,9 @@ __global__ void __launch_bounds__(NW * 32, (R1 == 16 || NW > 8) ? 1 : 2) feat_wa
 #endif
 
 // ---- host side: table blob, support check, launch -------------------------------------------------
-inline int warp8_radix(const dspx_plan *pl) { return pl->P == 512 ? 4 : (pl->P == 1024 ? 8 : (pl->P == 2048 ? 16 : 0)); }
+// n_fft 4096 runs the 2048-point machinery (radix 16) on the even and the odd samples of a frame at once
+inline bool warp8_x2(const dspx_plan *pl) { return pl->P == 4096; }
+inline int warp8_radix(const dspx_plan *pl) { return pl->P == 512 ? 4 : (pl->P == 1024 ? 8 : ((pl->P == 2048 || pl->P == 4096) ? 16 : 0)); }
 
 inline bool warp8_supported(const dspx_plan *pl)
 {
@@ -1026,8 +1037,10 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
 {
     const HostTables &h = pl->host;
     const int R1 = warp8_radix(pl), M = 64 * R1, P = 2 * M, J = 8 * R1;
-    const int n_mels = pl->cfg.n_mels, n_mfcc = pl->cfg.n_mfcc, n_bins = M + 1;
+    const bool x2 = warp8_x2(pl);                           // then P = 2048 is the length of each half-rate sequence
+    const int n_mels = pl->cfg.n_mels, n_mfcc = pl->cfg.n_mfcc, n_bins = x2 ? 2 * M + 1 : M + 1;
     const int units = R1 >= 8 ? R1 / 8 : 1;
+    tb.x2 = x2 ? 1 : 0;
     // --- mel chunks from the bin view: runs of equal g, cut into chunks of 8 bins ---
     struct Chunk { int run, start, count; };
     std::vector<Chunk> chunks;
@@ -1061,6 +1074,9 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     tb.tw2 = off; off += al4(7 * 8 * 2);
     tb.ptw = off; off += units * 9 * 32 * 2;
     tb.ppos = off; off += units * 9 * 32 * 2;
+    tb.win4 = off; off += x2 ? 2 * R1 * 32 * 4 : 0;
+    tb.ptw2 = off; off += x2 ? units * 9 * 32 * 2 : 0;
+    tb.ppos4 = off; off += x2 ? units * 9 * 32 * 4 : 0;
     tb.cw = off; off += tb.n_slots * W8_WROW;
     tb.cflag = off; off += tb.n_slots;
     tb.fdesc = off; off += n_mels * 4;
@@ -1068,7 +1084,24 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     tb.total = al4(off);
     blob.assign(tb.total, 0.f);
     const double two_pi = 2.0 * M_PI;
-    for (int s = 0; s < 2; s++)
+    if (x2) {
+        const int take = std::min(pl->cfg.frame_length, 2 * P);
+        for (int s = 0; s < 2; s++)
+            for (int a = 0; a < R1; a++)
+                for (int l = 0; l < 32; l++)
+                    for (int j = 0; j < 4; j++) {
+                        const int n = 4 * ((l + 32 * s) + 64 * a) + j;   // sample of the 4096-point frame
+                        blob[tb.win4 + ((s * R1 + a) * 32 + l) * 4 + j] = n < take ? (float)(0.5 * h.window[n]) : 0.f;
+                    }
+        for (int w = 0; w < units; w++)
+            for (int m = 0; m < 9; m++)
+                for (int l = 0; l < 32; l++) {
+                    const double ang = -two_pi * (double)w8_bin(J, l + 32 * w, m) / (double)(2 * P);
+                    blob[tb.ptw2 + ((w * 9 + m) * 32 + l) * 2] = (float)std::cos(ang);
+                    blob[tb.ptw2 + ((w * 9 + m) * 32 + l) * 2 + 1] = (float)std::sin(ang);
+                }
+    }
+    for (int s = 0; s < 2 && !x2; s++)
         for (int a = 0; a < R1; a++)
             for (int l = 0; l < 32; l++) {
                 const int n = 128 * a + 2 * (l + 32 * s);
@@ -1104,7 +1137,7 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     int seg = 0;
     for (int ci = 0; ci < n_chunks; ci++) {
         const Chunk &ch = chunks[ci];
-        const int rot = ((ci / rounds) >> 1) & 3;          // rotation used by the lane that owns this chunk
+        const int rot = x2 ? 0 : ((ci / rounds) >> 1) & 3;  // rotation used by the lane that owns this chunk
         for (int j = 0; j < ch.count; j++) {
             const int k = ch.start + j;
             pos[k] = W8_CSTRIDE * ci + j;
@@ -1145,9 +1178,9 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         const int sg = cflag[ci] >> 8;
         cflag[ci] = (cflag[ci] & 3) | (slot_a[sg] << 8) | (int32_t)((uint32_t)slot_b[sg] << 20);
     }
-    tb.tile_floats = std::max(4 * M, 2 * (W8_CSTRIDE * tb.n_slots + 16 + tb.seg_slots + parts * tb.lm_part + 32)) + 16;
+    tb.tile_floats = std::max(4 * M, (x2 ? 1 : 2) * (W8_CSTRIDE * tb.n_slots + 16) + 2 * (tb.seg_slots + parts * tb.lm_part + 32)) + 16;
     int32_t *ppos = reinterpret_cast<int32_t *>(blob.data() + tb.ppos);
-    for (int w = 0; w < units; w++)
+    for (int w = 0; w < units && !x2; w++)
         for (int m = 0; m < 9; m++)
             for (int l = 0; l < 32; l++) {
                 int k = w8_bin(J, l + 32 * w, m);
@@ -1155,6 +1188,22 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
                 ppos[((w * 9 + m) * 32 + l) * 2] = pos[k];
                 ppos[((w * 9 + m) * 32 + l) * 2 + 1] = pos[M - k];
             }
+    if (x2) {
+        // slot (unit, m) of the sequence transforms holds bin k and its mirror M - k; the radix-2 combination turns them
+        // into the four bins k, 2M - k, M - k, M + k of the 4096-point transform (one float each in the tile)
+        int32_t *p4 = reinterpret_cast<int32_t *>(blob.data() + tb.ppos4);
+        for (int w = 0; w < units; w++)
+            for (int m = 0; m < 9; m++)
+                for (int l = 0; l < 32; l++) {
+                    int k = w8_bin(J, l + 32 * w, m);
+                    if (k > M) k = 0;
+                    int32_t *q = p4 + ((w * 9 + m) * 32 + l) * 4;
+                    q[0] = pos[k];
+                    q[1] = pos[2 * M - k];
+                    q[2] = pos[M - k];
+                    q[3] = pos[M + k];
+                }
+    }
     int32_t *fdesc = reinterpret_cast<int32_t *>(blob.data() + tb.fdesc);
     for (int g = 0; g < n_mels; g++) {
         fdesc[4 * g] = f_first[g];
@@ -1197,11 +1246,11 @@ inline int warp8_prepare(dspx_plan *pl)
     auto *pd = new W8PlanData();
     pd->tb = tb;
     pd->smem = smem;
-    pd->ctas_per_sm = (tb.r1 != 16 && smem * 2 + 2048 <= 227 * 1024) ? 2 : 1;
+    pd->ctas_per_sm = (tb.r1 != 16 && smem * 2 + 2048 <= 227 * 1024) ? 2 : 1;   // (x2 plans have r1 = 16: one CTA)
     const size_t wide = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_WIDE);
     pd->smem_wide = (tb.r1 != 16 && wide + 1024 <= 227 * 1024 && !getenv("DSPX_W8_NARROW")) ? wide : 0;
     const size_t r16 = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_R16);
-    pd->smem_r16 = (tb.r1 == 16 && W8_WARPS_R16 > W8_WARPS && r16 + 1024 <= 227 * 1024) ? r16 : 0;
+    pd->smem_r16 = (tb.r1 == 16 && !tb.x2 && W8_WARPS_R16 > W8_WARPS && r16 + 1024 <= 227 * 1024) ? r16 : 0;
     pd->share = (2 * pl->cfg.hop_length == pl->P) && pl->cfg.frame_length == pl->P && !getenv("DSPX_W8_NOSHARE");
     pl->fast_host = pd;
     DSPX_CUDA_CHECK(cudaMalloc(&pl->d_fast_tables, blob.size() * sizeof(float)));

@@ -161,7 +161,8 @@ def test_warp8_kernel_replay_matches_reference(built, golden_small):
         rc = lib.emu_features_warp8(C.byref(cfg), fp(clips), C.c_int64(3), C.c_int64(clips.shape[1]),
                                     C.c_int64(clips.shape[1]), fp(lm), fp(mf), None, 0)
         n_fft = 1 << ((m["n_fft"] or m["frame_length"]) - 1).bit_length()              # mfcc.py:89-91
-        supported = n_fft in (512, 1024, 2048)            # frames shorter / longer than n_fft run the general variant
+        supported = n_fft in (512, 1024, 2048, 4096)      # frames shorter / longer than n_fft run the general variant;
+                                                          # 4096 = even / odd halves in the packed lanes (feat_warp8_x2.cuh)
         assert (rc == 0) == supported, (ci, rc)
         if rc != 0:
             continue
@@ -169,7 +170,7 @@ def test_warp8_kernel_replay_matches_reference(built, golden_small):
         for b in range(3):
             assert rel_err(mf[b], z[f"c{ci}_mfcc_{b}"]) < 1e-5, (ci, b)
             assert rel_err(lm[b], z[f"c{ci}_logmel_{b}"]) < 1e-5, (ci, b)
-    assert covered >= 18
+    assert covered >= 19
 
 
 def test_pcm16_quotient_is_exact(built):
