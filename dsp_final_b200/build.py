@@ -40,8 +40,9 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     OUT.mkdir(exist_ok=True)
     lib = OUT / "libdspx.so"
     if force or _stale(lib):
+        # -split-compile 0: ptxas works on the ~90 kernel instantiations in parallel (3x shorter build, same code per kernel)
         cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "128", "-Xcompiler", "-fPIC", "-shared",
-               "-o", str(lib), str(CSRC / "dspx.cu")]
+               "-split-compile", "0", "-o", str(lib), str(CSRC / "dspx.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
