@@ -41,6 +41,7 @@ constexpr int W8_WARPS_WIDE = DSPX_W8_WIDE;
 #ifndef DSPX_W8_R16
 #define DSPX_W8_R16 10
 #endif
+constexpr int W8_WARPS_MID = 12;         // tables and tiles too large for 20 warps (128 mels): one 12-warp CTA instead of one of 8
 constexpr int W8_WARPS_R16 = DSPX_W8_R16;           // n_fft 2048: one CTA per SM with as many 16 KB tiles as fit beside the tables         // or one 20-warp CTA per SM (<= 102 registers): more warps in flight to
                                           // cover the shared-memory pipe; +6 % on the feature path, worse for STFT mode
 
@@ -221,7 +222,7 @@ struct W8Ctx {               // everything one warp needs for one frame pair
     const int4 *ppos4;
     const float *cw;
     const int *cflag;
-    const int4 *fdesc;
+    const int2 *fdesc;       // {first slot, count} of every filter's run-piece sums
     const float *dct;
     float4 *xbuf;
     float2 *pbuf, *seg, *lm, *dsc;
@@ -251,6 +252,10 @@ DSPX_HD int w8_warp_floats(const W8Tables &tb, int n_mels)
     return (tb.tile_floats + 3) & ~3;
 }
 
+// distance (float2 slots) between the two part rows of the log-mel row: = 8 (mod 16), so the 64-bit stores of the
+// even filters (part 0) and the odd filters (part 1) of a half-warp fall into different halves of the bank space
+DSPX_HD int w8_lm_stride(int lm_part) { return ((lm_part + 7) & ~15) + 8; }
+
 DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, int n_mels, W8Ctx &c)
 {
     c.win = reinterpret_cast<const float2 *>(tables_smem + tb.win);
@@ -263,14 +268,14 @@ DSPX_HD void w8_carve(float *tables_smem, float *warp_smem, const W8Tables &tb, 
     c.ppos4 = reinterpret_cast<const int4 *>(tables_smem + tb.ppos4);
     c.cw = tables_smem + tb.cw;
     c.cflag = reinterpret_cast<const int *>(tables_smem + tb.cflag);
-    c.fdesc = reinterpret_cast<const int4 *>(tables_smem + tb.fdesc);
+    c.fdesc = reinterpret_cast<const int2 *>(tables_smem + tb.fdesc);
     c.dct = tables_smem + tb.dct;
     c.xbuf = reinterpret_cast<float4 *>(warp_smem);
     c.pbuf = reinterpret_cast<float2 *>(warp_smem);
     // power tile: float2 (frame A, frame B) per bin, or one float per bin in the x2 (single frame) mode
     c.seg = c.pbuf + (tb.x2 ? (W8_CSTRIDE * tb.n_slots + 16) / 2 : (W8_CSTRIDE * tb.n_slots + 16));
     c.lm = c.seg + tb.seg_slots;                             // seg_slots is even: 16-byte aligned for the DCT's 128-bit loads
-    c.dsc = c.lm + (32 / tb.cw_lanes) * tb.lm_part;
+    c.dsc = c.lm + (32 / tb.cw_lanes) * w8_lm_stride(tb.lm_part);
 }
 
 // ---- window and first-pass twiddles without table loads (R1 <= 8) ---------------------------------------
@@ -670,6 +675,15 @@ DSPX_HD void w8_store_power(const W8Ctx &c, int lane, int w, const W8Power &pw)
 // the half of a 128-byte line and the lane reads its four 16-byte pieces rotated by (lane >> 1) & 3:
 // the 128-bit loads of 8 neighbouring lanes hit 8 different bank groups (rounds is odd, so parity
 // alternates with the lane).  The weight rows (80 B apart) are stored pre-rotated to match.
+// Tile row of chunk ch = lane * rounds + r.  Neighbouring lanes must read rows of different parity (the two 64-byte
+// halves of a 128-byte line): with an odd number of rounds the chunk index itself alternates, with an even number
+// odd lanes swap their rows pairwise.
+DSPX_HD int w8_chunk_row(int ch, int lane, int rounds) { return ch ^ (lane & ~rounds & 1); }
+// The flag words (4 B) and weight rows (80 B) of a lane's chunks are consecutive; with an even number of rounds one
+// more word / 16-byte unit per lane keeps the lane stride odd (conflict-free 32-bit and 128-bit loads).
+DSPX_HD int w8_flag_index(int ch, int lane, int rounds) { return ch + (lane & -(~rounds & 1)); }
+DSPX_HD int w8_cw_index(int ch, int lane, int rounds) { return ch * W8_WROW + 4 * (lane & -(~rounds & 1)); }
+
 struct W8MelIn {                 // one chunk's operands: four 16-byte pieces of power values and of weights, and its flag word
     float4 p[4], w[4];
     int flag;
@@ -678,9 +692,9 @@ struct W8MelIn {                 // one chunk's operands: four 16-byte pieces of
 DSPX_HD void w8_mel_load(const W8Ctx &c, int lane, int r, W8MelIn &in)
 {
     const int ch = lane * c.rounds + r;
-    in.flag = c.cflag[ch];                                              // bit0 first, bit1 last, 8..19 / 20..31 slots of the sums
-    const float4 *pp = reinterpret_cast<const float4 *>(c.pbuf + ch * W8_CSTRIDE);
-    const float4 *ww = reinterpret_cast<const float4 *>(c.cw + ch * W8_WROW);
+    in.flag = c.cflag[w8_flag_index(ch, lane, c.rounds)];               // bit0 first, bit1 last, 8..19 / 20..31 slots of the sums
+    const float4 *pp = reinterpret_cast<const float4 *>(c.pbuf + w8_chunk_row(ch, lane, c.rounds) * W8_CSTRIDE);
+    const float4 *ww = reinterpret_cast<const float4 *>(c.cw + w8_cw_index(ch, lane, c.rounds));
     const int rot = (lane >> 1) & 3;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -760,12 +774,12 @@ DSPX_HD float2 w8_filter_sum(const W8Ctx &c, int2 d)
     return add2(s0, s1);
 }
 
-// The row kept for the DCT is stored part-major -- slot (f % parts) * lm_part + f / parts with parts = 32 / cw_lanes --
+// The row kept for the DCT is stored part-major -- slot (f % parts) * w8_lm_stride(lm_part) + f / parts with parts = 32 / cw_lanes --
 // so that a DCT lane finds the filters it sums in consecutive slots; slots past n_mels are zeroed (the table is
 // zero there too, but the tile still holds FFT data).  Two filters per lane are in flight at a time.
 DSPX_HD void w8_logmel_one(const W8Ctx &c, int f, int psh, float2 s)
 {
-    const int slot = ((f & psh) ? c.lm_part : 0) + (f >> psh);
+    const int slot = ((f & psh) ? w8_lm_stride(c.lm_part) : 0) + (f >> psh);
     if (f >= c.n_mels) {                                                // padding of the part rows
         c.lm[slot] = make_float2(0.f, 0.f);
         return;
@@ -782,10 +796,10 @@ DSPX_HD void w8_logmel(const W8Ctx &c, int lane)
 {
     const int psh = c.cw_lanes == 16 ? 1 : 0;                           // log2(parts)
     const int n_slots = c.lm_part << psh;
-    const int2 *fd = reinterpret_cast<const int2 *>(c.fdesc);           // {first slot, count} at stride 2
+    const int2 *fd = c.fdesc;
     for (int f0 = lane; f0 < n_slots; f0 += 64) {
         const int f1 = f0 + 32;
-        const int2 d0 = fd[2 * (f0 < c.n_mels ? f0 : 0)], d1 = fd[2 * (f1 < c.n_mels ? f1 : 0)];
+        const int2 d0 = fd[f0 < c.n_mels ? f0 : 0], d1 = fd[f1 < c.n_mels ? f1 : 0];
         const float2 s0 = w8_filter_sum(c, d0), s1 = w8_filter_sum(c, d1);
         w8_logmel_one(c, f0, psh, s0);
         if (f1 < n_slots) w8_logmel_one(c, f1, psh, s1);
@@ -803,7 +817,7 @@ DSPX_HD float2 w8_dct_partial(const W8Ctx &c, int lane, int c0)
     const int q = lane & (c.cw_lanes - 1), part = lane >> sh;
     const int blk = c0 >> sh;                                               // c0 is a multiple of cw_lanes
     const float4 *col = reinterpret_cast<const float4 *>(c.dct + (size_t)(blk * 32 + part * c.cw_lanes + q) * c.dct_row);
-    const float4 *lm = reinterpret_cast<const float4 *>(c.lm + part * c.lm_part);
+    const float4 *lm = reinterpret_cast<const float4 *>(c.lm + part * w8_lm_stride(c.lm_part));
     float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
     const int n4 = c.lm_part >> 2;                                          // whole groups of four filters
 #pragma unroll 5
@@ -1033,6 +1047,135 @@ inline bool warp8_supported(const dspx_plan *pl)
            pl->cfg.n_mels <= 256 && pl->cfg.n_mfcc <= 128 && pl->host.two_band_ok;
 }
 
+
+// ---- bank-conflict-free table layouts (host side) -------------------------------------------------------
+// 64-bit shared-memory accesses are served per half-warp, one wavefront per set of lanes that touch 16 different
+// 8-byte bank pairs (slot mod 16); ncu's per-instruction wavefront counts of the round-1 layout follow this model
+// exactly (profiles/r02_warp8_layout.md).  Two layouts are chosen with it when the plan is built:
+//
+//  * which of the 8 slots of its chunk row a bin occupies.  Bins are the edges of a bipartite graph between chunk
+//    rows and (store instruction, half-warp, row parity) groups; both kinds of node need pairwise different slots on
+//    their edges, and a bipartite graph with degrees <= 8 always has such an edge colouring with 8 colours (Koenig):
+//    every power store then takes its minimum of two wavefronts.
+//  * where the run-piece sums of every filter sit (w8_seg_layout below).
+inline void w8_edge_colour(int na, int nb, const std::vector<std::pair<int, int>> &edges, int ncol, std::vector<int> &colour)
+{
+    std::vector<int> ea((size_t)na * ncol, -1), eb((size_t)nb * ncol, -1);     // edge that uses colour c at a node
+    colour.assign(edges.size(), -1);
+    for (size_t e = 0; e < edges.size(); e++) {
+        const int a = edges[e].first, b = edges[e].second;
+        int ca = -1, cb = -1;
+        for (int c = ncol - 1; c >= 0; c--) {
+            if (ea[(size_t)a * ncol + c] < 0) ca = c;
+            if (eb[(size_t)b * ncol + c] < 0) cb = c;
+        }
+        if (ca < 0 || cb < 0) continue;                                        // an over-full node: left to the caller
+        if (eb[(size_t)b * ncol + ca] >= 0) {
+            // ca is taken at b: swap ca <-> cb along the alternating path that starts there (it cannot reach a)
+            std::vector<int> path;
+            int node = b, want = ca;
+            bool at_b = true;
+            for (;;) {
+                const int nxt = at_b ? eb[(size_t)node * ncol + want] : ea[(size_t)node * ncol + want];
+                if (nxt < 0) break;
+                path.push_back(nxt);
+                node = at_b ? edges[nxt].first : edges[nxt].second;
+                at_b = !at_b;
+                want = want == ca ? cb : ca;
+            }
+            for (int pe : path) {
+                ea[(size_t)edges[pe].first * ncol + colour[pe]] = -1;
+                eb[(size_t)edges[pe].second * ncol + colour[pe]] = -1;
+            }
+            for (int pe : path) {
+                colour[pe] = colour[pe] == ca ? cb : ca;
+                ea[(size_t)edges[pe].first * ncol + colour[pe]] = pe;
+                eb[(size_t)edges[pe].second * ncol + colour[pe]] = pe;
+            }
+        }
+        colour[e] = ca;
+        ea[(size_t)a * ncol + ca] = (int)e;
+        eb[(size_t)b * ncol + ca] = (int)e;
+    }
+}
+
+// wavefronts of one 64-bit access of a warp: slots[lane] in 8-byte units, < 0 = lane inactive
+inline int w8_wavefronts64(const int *slots)
+{
+    int total = 0;
+    for (int h = 0; h < 2; h++) {
+        int seen[16][16], cnt[16] = {0}, worst = 0;
+        for (int l = 16 * h; l < 16 * h + 16; l++) {
+            const int sl = slots[l];
+            if (sl < 0) continue;
+            const int b = sl & 15;
+            bool dup = false;
+            for (int i = 0; i < cnt[b]; i++) dup = dup || seen[b][i] == sl;
+            if (!dup) seen[b][cnt[b]++] = sl;
+            worst = std::max(worst, cnt[b]);
+        }
+        total += worst;
+    }
+    return total;
+}
+
+// One value a filter sums: the `a` or `b` sum of run piece (segment) seg, stored by `lane` in round `round`.
+struct W8SegEntry { int seg, is_b, lane, round; };
+
+// Slots of the run-piece sums.  Filter g reads its entries from consecutive slots starting at an even one
+// (w8_filter_sum: 128-bit loads); the lanes that end a run piece in round r store their sums there (two 64-bit
+// stores per round).  Starts are placed so that the 16-byte units of 8 consecutive filters differ mod 8 (the loads
+// of a quarter-warp are conflict-free), the order inside each filter by a pairwise-swap descent on the modelled
+// wavefronts of the stores.
+inline void w8_seg_layout(const std::vector<std::vector<W8SegEntry>> &filt, int rounds, std::vector<int> &f_first,
+                          std::vector<std::vector<int>> &order, int &end_slot)
+{
+    const int n = (int)filt.size();
+    f_first.assign(n, 0);
+    order.assign(n, {});
+    int slot = 0;
+    for (int g = 0; g < n; g++) {
+        slot = (slot + 1) & ~1;
+        if (!filt[g].empty()) {
+            for (int tries = 0; tries < 8; tries++, slot += 2) {
+                bool clash = false;
+                for (int o = g - (g & 7); o < g; o++) clash = clash || (!filt[o].empty() && ((f_first[o] >> 1) & 7) == ((slot >> 1) & 7));
+                if (!clash) break;
+            }
+        }
+        f_first[g] = slot;
+        slot += (int)filt[g].size();
+        for (int i = 0; i < (int)filt[g].size(); i++) order[g].push_back(i);
+    }
+    end_slot = slot;
+    auto cost = [&]() {
+        std::vector<int> slots((size_t)rounds * 2 * 32, -1);
+        for (int g = 0; g < n; g++)
+            for (int j = 0; j < (int)order[g].size(); j++) {
+                const W8SegEntry &e = filt[g][order[g][j]];
+                slots[((size_t)e.round * 2 + e.is_b) * 32 + e.lane] = f_first[g] + j;
+            }
+        int c = 0;
+        for (int i = 0; i < rounds * 2; i++) c += w8_wavefronts64(&slots[(size_t)i * 32]);
+        return c;
+    };
+    int best = cost();
+    for (int pass = 0; pass < 6; pass++) {
+        bool improved = false;
+        for (int g = 0; g < n; g++) {
+            const int m = (int)order[g].size();
+            for (int i = 0; i < m; i++)
+                for (int j = i + 1; j < m; j++) {
+                    std::swap(order[g][i], order[g][j]);
+                    const int c = cost();
+                    if (c < best) { best = c; improved = true; }
+                    else std::swap(order[g][i], order[g][j]);
+                }
+        }
+        if (!improved) break;
+    }
+}
+
 inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8Tables &tb)
 {
     const HostTables &h = pl->host;
@@ -1057,7 +1200,7 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     }
     const int n_chunks = (int)chunks.size();
     int rounds = std::max(1, (n_chunks + 31) / 32);
-    if (rounds % 2 == 0) rounds++;                       // odd: lanes' 80-byte rows stay conflict-free
+    if (x2 && rounds % 2 == 0) rounds++;                 // the x2 reader has no row swap (w8_chunk_row): odd rounds only
     tb.r1 = R1;
     tb.rounds = rounds;
     tb.n_slots = 32 * rounds;
@@ -1077,9 +1220,9 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     tb.win4 = off; off += x2 ? 2 * R1 * 32 * 4 : 0;
     tb.ptw2 = off; off += x2 ? units * 9 * 32 * 2 : 0;
     tb.ppos4 = off; off += x2 ? units * 9 * 32 * 4 : 0;
-    tb.cw = off; off += tb.n_slots * W8_WROW;
-    tb.cflag = off; off += tb.n_slots;
-    tb.fdesc = off; off += n_mels * 4;
+    tb.cw = off; off += tb.n_slots * W8_WROW + 32 * 4;     // + the lane skew of even round counts (w8_cw_index)
+    tb.cflag = off; off += tb.n_slots + 32;
+    tb.fdesc = off; off += al4(n_mels * 2);
     tb.dct = off; off += dct_blocks * 32 * tb.dct_row;
     tb.total = al4(off);
     blob.assign(tb.total, 0.f);
@@ -1129,46 +1272,92 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
                 blob[tb.ptw + ((w * 9 + m) * 32 + l) * 2] = (float)std::cos(ang);
                 blob[tb.ptw + ((w * 9 + m) * 32 + l) * 2 + 1] = (float)std::sin(ang);
             }
-    // chunk c lives at (lane = c / rounds, round = c % rounds); its bins sit at tile slots 10c .. 10c+7
+    // chunk c lives at (lane = c / rounds, round = c % rounds); its bins sit in the row of tile slots 8c .. 8c+7
     std::vector<int> pos(n_bins, W8_CSTRIDE * tb.n_slots + 8);          // dump slot for unused bins
-    int32_t *cflag = reinterpret_cast<int32_t *>(blob.data() + tb.cflag);
+    std::vector<int> chunk_of(n_bins, -1), slot_of(n_bins, -1);
+    for (int ci = 0; ci < n_chunks; ci++)
+        for (int j = 0; j < chunks[ci].count; j++) {
+            chunk_of[chunks[ci].start + j] = ci;
+            slot_of[chunks[ci].start + j] = j;
+        }
+    if (!x2) {
+        // slot of every bin inside its row: edge colouring of (chunk row) x (store instruction, half-warp, row parity)
+        std::vector<std::pair<int, int>> edges;
+        std::vector<int> edge_bin;
+        std::vector<char> seen(n_bins, 0);
+        const int active = R1 >= 8 ? 32 : 16;
+        for (int w = 0; w < units; w++)
+            for (int m = 0; m < 8; m++)
+                for (int sdx = 0; sdx < 2; sdx++)
+                    for (int l = 0; l < active; l++) {
+                        const int k0 = w8_bin(J, l + 32 * w, m);
+                        if (k0 > M) continue;
+                        const int k = sdx ? M - k0 : k0;
+                        if (chunk_of[k] < 0 || seen[k]) continue;          // a self-mirrored bin is stored twice: first store counts
+                        seen[k] = 1;
+                        const int group = ((w * 8 + m) * 2 + sdx) * 2 + (l >> 4);
+                        edges.push_back({chunk_of[k], group * 2 + (w8_chunk_row(chunk_of[k], chunk_of[k] / rounds, rounds) & 1)});
+                        edge_bin.push_back(k);
+                    }
+        std::vector<int> colour;
+        w8_edge_colour(n_chunks, units * 8 * 2 * 2 * 2, edges, W8_CHUNK, colour);
+        std::vector<int> used(n_chunks, 0);
+        for (int k = 0; k < n_bins; k++) slot_of[k] = -1;
+        for (size_t e = 0; e < edges.size(); e++)
+            if (colour[e] >= 0) { slot_of[edge_bin[e]] = colour[e]; used[edges[e].first] |= 1 << colour[e]; }
+        for (int k = 0; k < n_bins; k++)                                  // over-full groups, bins only lane 0's ninth slot stores
+            if (chunk_of[k] >= 0 && slot_of[k] < 0) {
+                int c = 0;
+                while (used[chunk_of[k]] & (1 << c)) c++;
+                slot_of[k] = c;
+                used[chunk_of[k]] |= 1 << c;
+            }
+    }
+    std::vector<int32_t> cflag(tb.n_slots, 0);
     const int n_runs = (int)run_g.size();
     std::vector<int> seg_first(n_runs, 0), seg_cnt(n_runs, 0);
+    std::vector<int> seg_chunk;                                          // chunk that ends (and stores) each run piece
     int seg = 0;
     for (int ci = 0; ci < n_chunks; ci++) {
         const Chunk &ch = chunks[ci];
         const int rot = x2 ? 0 : ((ci / rounds) >> 1) & 3;  // rotation used by the lane that owns this chunk
         for (int j = 0; j < ch.count; j++) {
-            const int k = ch.start + j;
-            pos[k] = W8_CSTRIDE * ci + j;
-            const int piece = (((j >> 1) - rot) & 3), jj = 2 * piece + (j & 1);      // where the lane meets bin j
-            blob[tb.cw + ci * W8_WROW + 2 * jj] = h.bin_wfall[k];
-            blob[tb.cw + ci * W8_WROW + 2 * jj + 1] = h.bin_wrise[k];
+            const int k = ch.start + j, sl = slot_of[k];
+            pos[k] = W8_CSTRIDE * w8_chunk_row(ci, ci / rounds, rounds) + sl;
+            const int piece = (((sl >> 1) - rot) & 3), jj = 2 * piece + (sl & 1);    // where the lane meets the bin in slot sl
+            blob[tb.cw + w8_cw_index(ci, ci / rounds, rounds) + 2 * jj] = h.bin_wfall[k];
+            blob[tb.cw + w8_cw_index(ci, ci / rounds, rounds) + 2 * jj + 1] = h.bin_wrise[k];
         }
         const bool first = (ci % rounds == 0) || chunks[ci - 1].run != ch.run;
         const bool last = (ci % rounds == rounds - 1) || ci == n_chunks - 1 || chunks[ci + 1].run != ch.run;
         if (first && seg_cnt[ch.run] == 0) seg_first[ch.run] = seg;
         cflag[ci] = (first ? 1 : 0) | (last ? 2 : 0) | (seg << 8);
-        if (last) { seg_cnt[ch.run]++; seg++; }
+        if (last) { seg_cnt[ch.run]++; seg++; seg_chunk.push_back(ci); }
     }
     tb.n_segs = std::max(seg, 1);
-    // slots of the sums: filter g reads [b sums of run g-1][a sums of run g] as one contiguous range that starts
-    // at an even slot (16-byte aligned for w8_filter_sum's 128-bit loads)
+    // slots of the sums: filter g reads the b sums of run g-1 and the a sums of run g as one contiguous range
     std::vector<int> run_of_filter(n_mels + 1, -1);
     for (int r = 0; r < n_runs; r++)
         if (run_g[r] >= 0 && run_g[r] <= n_mels) run_of_filter[run_g[r]] = r;
-    std::vector<int> f_first(n_mels, 0), f_cnt(n_mels, 0);
-    std::vector<int> slot_a(tb.n_segs, -1), slot_b(tb.n_segs, -1);
-    int slot = 0;
+    std::vector<std::vector<W8SegEntry>> filt(n_mels);
     for (int g = 0; g < n_mels; g++) {
-        slot = (slot + 1) & ~1;
-        f_first[g] = slot;
         const int rb = g >= 1 ? run_of_filter[g - 1] : -1, ra = run_of_filter[g];
-        if (rb >= 0) for (int i = 0; i < seg_cnt[rb]; i++) slot_b[seg_first[rb] + i] = slot++;
-        if (ra >= 0) for (int i = 0; i < seg_cnt[ra]; i++) slot_a[seg_first[ra] + i] = slot++;
-        f_cnt[g] = slot - f_first[g];
+        if (rb >= 0) for (int i = 0; i < seg_cnt[rb]; i++) { const int sg = seg_first[rb] + i; filt[g].push_back({sg, 1, seg_chunk[sg] / rounds, seg_chunk[sg] % rounds}); }
+        if (ra >= 0) for (int i = 0; i < seg_cnt[ra]; i++) { const int sg = seg_first[ra] + i; filt[g].push_back({sg, 0, seg_chunk[sg] / rounds, seg_chunk[sg] % rounds}); }
     }
-    const int dump = (slot + 1) & ~1;                     // sums no filter reads (b of the last run, a of run -1) land here
+    std::vector<int> f_first, f_cnt(n_mels, 0);
+    std::vector<std::vector<int>> order;
+    int end_slot = 0;
+    w8_seg_layout(filt, rounds, f_first, order, end_slot);
+    std::vector<int> slot_a(tb.n_segs, -1), slot_b(tb.n_segs, -1);
+    for (int g = 0; g < n_mels; g++) {
+        f_cnt[g] = (int)filt[g].size();
+        for (int j = 0; j < f_cnt[g]; j++) {
+            const W8SegEntry &e = filt[g][order[g][j]];
+            (e.is_b ? slot_b : slot_a)[e.seg] = f_first[g] + j;
+        }
+    }
+    const int dump = (end_slot + 1) & ~1;                 // sums no filter reads (b of the last run, a of run -1) land here
     tb.seg_slots = dump + 8;                              // + the dump slot and room for the 6-slot reads of the last filter
     for (int i = 0; i < tb.n_segs; i++) {
         if (slot_a[i] < 0) slot_a[i] = dump;
@@ -1178,7 +1367,9 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
         const int sg = cflag[ci] >> 8;
         cflag[ci] = (cflag[ci] & 3) | (slot_a[sg] << 8) | (int32_t)((uint32_t)slot_b[sg] << 20);
     }
-    tb.tile_floats = std::max(4 * M, (x2 ? 1 : 2) * (W8_CSTRIDE * tb.n_slots + 16) + 2 * (tb.seg_slots + parts * tb.lm_part + 32)) + 16;
+    for (int ci = 0; ci < tb.n_slots; ci++)
+        reinterpret_cast<int32_t *>(blob.data() + tb.cflag)[w8_flag_index(ci, ci / rounds, rounds)] = cflag[ci];
+    tb.tile_floats = std::max(4 * M, (x2 ? 1 : 2) * (W8_CSTRIDE * tb.n_slots + 16) + 2 * (tb.seg_slots + parts * w8_lm_stride(tb.lm_part) + 32)) + 16;
     int32_t *ppos = reinterpret_cast<int32_t *>(blob.data() + tb.ppos);
     for (int w = 0; w < units && !x2; w++)
         for (int m = 0; m < 9; m++)
@@ -1206,8 +1397,8 @@ inline void warp8_build_tables(const dspx_plan *pl, std::vector<float> &blob, W8
     }
     int32_t *fdesc = reinterpret_cast<int32_t *>(blob.data() + tb.fdesc);
     for (int g = 0; g < n_mels; g++) {
-        fdesc[4 * g] = f_first[g];
-        fdesc[4 * g + 1] = f_cnt[g];
+        fdesc[2 * g] = f_first[g];
+        fdesc[2 * g + 1] = f_cnt[g];
     }
     // DCT table [block][part][q][dct_row]: row (part, q) holds coefficient block * cw_lanes + q for the filters
     // f = part, part + parts, ...; zero beyond n_mfcc and beyond n_mels
@@ -1232,6 +1423,7 @@ struct W8PlanData {
     int ctas_per_sm;
     size_t smem;
     size_t smem_wide;        // 0 when the 20-warp configuration does not fit
+    size_t smem_mid;         // shared memory of the W8_WARPS_MID-warp configuration (used when the wide one does not fit), or 0
     size_t smem_r16;         // n_fft 2048: shared memory of the W8_WARPS_R16-warp configuration, 0 when it does not fit
     bool share;              // hop == n_fft / 2: the two frames of a pair share rows (DSPX_W8_NOSHARE=1 at plan creation disables)
 };
@@ -1249,6 +1441,8 @@ inline int warp8_prepare(dspx_plan *pl)
     pd->ctas_per_sm = (tb.r1 != 16 && smem * 2 + 2048 <= 227 * 1024) ? 2 : 1;   // (x2 plans have r1 = 16: one CTA)
     const size_t wide = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_WIDE);
     pd->smem_wide = (tb.r1 != 16 && wide + 1024 <= 227 * 1024 && !getenv("DSPX_W8_NARROW")) ? wide : 0;
+    const size_t mid = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_MID);
+    pd->smem_mid = (tb.r1 != 16 && !pd->smem_wide && pd->ctas_per_sm == 1 && mid + 1024 <= 227 * 1024 && !getenv("DSPX_W8_NARROW")) ? mid : 0;
     const size_t r16 = warp8_smem_bytes(tb, pl->cfg.n_mels, W8_WARPS_R16);
     pd->smem_r16 = (tb.r1 == 16 && !tb.x2 && W8_WARPS_R16 > W8_WARPS && r16 + 1024 <= 227 * 1024) ? r16 : 0;
     pd->share = (2 * pl->cfg.hop_length == pl->P) && pl->cfg.frame_length == pl->P && !getenv("DSPX_W8_NOSHARE");
@@ -1289,6 +1483,13 @@ inline int w8_launch_cfg(const W8Params &p, const W8PlanData *pd, int device, in
         if (!STFT && p.eacc) return w8_launch_nw<R1, PRE, STFT, SHARE, NWW, !STFT>(p, pd->smem_wide, device, ctas, st);
         return w8_launch_nw<R1, PRE, STFT, SHARE, NWW>(p, pd->smem_wide, device, ctas, st);
     }
+    if (!STFT && R1 != 16 && pd->smem_mid) {
+        int64_t ctas = ((int64_t)p.n_items + W8_WARPS_MID - 1) / W8_WARPS_MID;
+        if (ctas > sm_count) ctas = sm_count;
+        constexpr int NWM = (R1 != 16 && !STFT) ? W8_WARPS_MID : W8_WARPS;
+        if (!STFT && p.eacc) return w8_launch_nw<R1, PRE, STFT, SHARE, NWM, !STFT>(p, pd->smem_mid, device, ctas, st);
+        return w8_launch_nw<R1, PRE, STFT, SHARE, NWM>(p, pd->smem_mid, device, ctas, st);
+    }
     if (!STFT && R1 == 16 && pd->smem_r16) {
         int64_t ctas = ((int64_t)p.n_items + W8_WARPS_R16 - 1) / W8_WARPS_R16;
         if (ctas > sm_count) ctas = sm_count;
@@ -1311,6 +1512,11 @@ inline int w8_launch_u4(const W8Params &p, const W8PlanData *pd, int device, int
         int64_t ctas = ((int64_t)p.n_items + W8_WARPS_WIDE - 1) / W8_WARPS_WIDE;
         if (ctas > sm_count) ctas = sm_count;
         return w8_launch_nw<R1, PRE, false, false, (R1 != 16) ? W8_WARPS_WIDE : W8_WARPS, false, true, PCM>(p, pd->smem_wide, device, ctas, st);
+    }
+    if (R1 != 16 && pd->smem_mid) {
+        int64_t ctas = ((int64_t)p.n_items + W8_WARPS_MID - 1) / W8_WARPS_MID;
+        if (ctas > sm_count) ctas = sm_count;
+        return w8_launch_nw<R1, PRE, false, false, (R1 != 16) ? W8_WARPS_MID : W8_WARPS, false, true, PCM>(p, pd->smem_mid, device, ctas, st);
     }
     if (R1 == 16 && pd->smem_r16) {
         int64_t ctas = ((int64_t)p.n_items + W8_WARPS_R16 - 1) / W8_WARPS_R16;
