@@ -139,6 +139,83 @@ int emu_features_generic(const dspx_config *cfg, const float *clips, int64_t n_c
     return DSPX_OK;
 }
 
+// Modelled shared-memory wavefronts of the table-driven accesses of feat_warp8_kernel (the model w8_wavefronts64 /
+// the quarter-warp rule for 128-bit loads; profiles/r02_warp8_layout.md compares it with ncu's per-instruction counts):
+// out = {power stores, their minimum, run-piece sum stores, their minimum, filter-sum loads, their minimum, rounds,
+//        bins that share a tile slot with another bin (must be 0)}
+int emu_warp8_layout(const dspx_config *cfg, int32_t *out)
+{
+    EmuTables e;
+    int rc = emu_build(cfg, e);
+    if (rc != DSPX_OK) return rc;
+    dspx_plan pl;
+    pl.cfg = *cfg;
+    pl.P = e.P;
+    pl.M = e.M;
+    pl.n_bins = e.n_bins;
+    pl.host = e.t;
+    if (!warp8_supported(&pl)) return DSPX_EUNSUPPORTED;
+    std::vector<float> blob;
+    W8Tables tb{};
+    warp8_build_tables(&pl, blob, tb);
+    if (tb.x2) return DSPX_EUNSUPPORTED;
+    const int units = tb.r1 >= 8 ? tb.r1 / 8 : 1, active = tb.r1 >= 8 ? 32 : 16, M = 64 * tb.r1, J = 8 * tb.r1;
+    const int32_t *ppos = reinterpret_cast<const int32_t *>(blob.data() + tb.ppos);
+    const int dump = W8_CSTRIDE * tb.n_slots + 8;
+    int pw = 0, pw_min = 0;
+    std::vector<int> owner(dump + 1, -1);
+    int shared_slots = 0;
+    for (int w = 0; w < units; w++)
+        for (int m = 0; m < 9; m++)
+            for (int s = 0; s < 2; s++) {
+                int a[32], n = 0;
+                for (int l = 0; l < 32; l++) {
+                    const bool on = l < active && (m < 8 || l + 32 * w == 0);
+                    a[l] = on ? ppos[((w * 9 + m) * 32 + l) * 2 + s] : -1;
+                    n += on;
+                    if (on && a[l] != dump) {
+                        const int k0 = w8_bin(J, l + 32 * w, m), k = s ? M - k0 : k0;
+                        if (owner[a[l]] >= 0 && owner[a[l]] != k) shared_slots++;
+                        owner[a[l]] = k;
+                    }
+                }
+                pw += w8_wavefronts64(a);
+                pw_min += (n > 16) ? 2 : (n > 0 ? 1 : 0);
+            }
+    const int32_t *cflag = reinterpret_cast<const int32_t *>(blob.data() + tb.cflag);
+    int sw = 0, sw_min = 0;
+    for (int r = 0; r < tb.rounds; r++)
+        for (int s = 0; s < 2; s++) {
+            int a[32], lo = 0, hi = 0;
+            for (int l = 0; l < 32; l++) {
+                const int fl = cflag[w8_flag_index(l * tb.rounds + r, l, tb.rounds)];
+                a[l] = (fl & 2) ? (s ? (int)((unsigned)fl >> 20) : ((fl >> 8) & 0xfff)) : -1;
+                if (a[l] >= 0) (l < 16 ? lo : hi)++;
+            }
+            sw += w8_wavefronts64(a);
+            sw_min += (lo > 0) + (hi > 0);
+        }
+    const int32_t *fd = reinterpret_cast<const int32_t *>(blob.data() + tb.fdesc);
+    const int psh = tb.cw_lanes == 16 ? 1 : 0, n_slots = tb.lm_part << psh;
+    int fl_wf = 0, fl_min = 0;
+    for (int base = 0; base < n_slots; base += 32)
+        for (int i = 0; i < 3; i++)
+            for (int q = 0; q < 4; q++) {                                   // 128-bit loads: a quarter-warp per wavefront
+                int units16[8], cnt[8] = {0}, worst = 0;
+                for (int l = 0; l < 8; l++) {
+                    const int f = base + 8 * q + l;
+                    units16[l] = fd[2 * (f < cfg->n_mels ? f : 0)] / 2 + i;
+                    bool dup = false;
+                    for (int o = 0; o < l; o++) dup = dup || units16[o] == units16[l];
+                    if (!dup) worst = std::max(worst, ++cnt[units16[l] & 7]);
+                }
+                fl_wf += worst;
+                fl_min += 1;
+            }
+    out[0] = pw; out[1] = pw_min; out[2] = sw; out[3] = sw_min; out[4] = fl_wf; out[5] = fl_min; out[6] = tb.rounds; out[7] = shared_slots;
+    return DSPX_OK;
+}
+
 // Replays feat_warp8_kernel: one "warp" at a time, each phase run for lanes 0..31 in turn
 // (a __syncwarp() separates the phases on the device).
 int emu_features_warp8(const dspx_config *cfg, const float *clips, int64_t n_clips, int64_t clip_len,

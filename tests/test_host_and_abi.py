@@ -219,6 +219,28 @@ def test_warp8_replay_full_clip(built, golden_config1):
     assert rel_err(mf[0], g["mfcc"]) < 1e-5 and rel_err(lm[0], g["logmel"]) < 1e-5
 
 
+def test_warp8_table_layouts_are_conflict_aware(built):
+    """The plan-time layouts of feat_warp8_kernel's tables (csrc/feat_warp8.cuh: w8_edge_colour, w8_seg_layout): no two
+    bins share a tile slot, the filter-sum loads are conflict-free under the bank model, and the modelled wavefronts of
+    the power stores stay below the round-1 layout's (59 for the headline configuration, measured by ncu)."""
+    lib, DspxConfig = _emu(built)
+    seen = {}
+    for fl in (512, 1024, 2048):
+        for n_mels in (40, 64, 128):
+            m = dict(sample_rate=44100, frame_length=fl, hop_length=fl // 2, n_fft=None, n_mels=n_mels, n_mfcc=13, f_min=0.0,
+                     f_max=None, pre_emphasis=0.97, window="hann")
+            cfg = _cfg_struct(DspxConfig, m, kernel=2)
+            out = (C.c_int32 * 8)()
+            assert lib.emu_warp8_layout(C.byref(cfg), out) == 0, (fl, n_mels)
+            pw, pw_min, sw, sw_min, fl_wf, fl_min, rounds, shared = list(out)
+            seen[(fl, n_mels)] = list(out)
+            assert shared == 0, (fl, n_mels)                     # every bin has its own slot
+            assert fl_wf == fl_min, (fl, n_mels, fl_wf, fl_min)   # 128-bit filter-sum loads: one wavefront per quarter-warp
+            assert pw_min <= pw <= 2 * pw_min and sw >= sw_min, (fl, n_mels, list(out))
+    assert seen[(1024, 40)][0] <= 52 and seen[(1024, 40)][6] == 3, seen[(1024, 40)]
+    assert seen[(512, 40)][6] == 2, seen[(512, 40)]              # even round counts are allowed (row swap for odd lanes)
+
+
 def test_kernel_replay_is_addresssanitizer_clean(tmp_path):
     """Out-of-bounds check of the kernels' index arithmetic: the CPU replay of both feature kernels
     (exact-size shared-memory tiles and outputs) under AddressSanitizer, 11 configurations.
