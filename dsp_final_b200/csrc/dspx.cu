@@ -993,7 +993,12 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
             cp.qf = qf_t;
             cp.dbf = dbf_t;
             cp.shared_thr = tp.n_splits > 1 ? shared_thr : nullptr;
-            if (cp.shared_thr) DSPX_CUDA_CHECK(cudaMemsetAsync(shared_thr, 0, (size_t)nq * 8, st));
+#ifdef DSPX_TC_PROFILE                  // profiling builds only: DSPX_EXPERIMENT_KEEP_THR=1 keeps the thresholds of the previous call (steady-state per-role cycles)
+            if (cp.shared_thr && !getenv("DSPX_EXPERIMENT_KEEP_THR"))
+#else
+            if (cp.shared_thr)
+#endif
+                DSPX_CUDA_CHECK(cudaMemsetAsync(shared_thr, 0, (size_t)nq * 8, st));
             dim3 cgrid((unsigned)qtiles, (unsigned)tp.n_splits);
             const size_t smem = topk_tc_smem_bytes(k);
             if (dim == 26) {
@@ -1038,6 +1043,10 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
 }
 
 #ifdef DSPX_TC_PROFILE
+extern "C" int dspx_debug_tc_trace(long long *out)       // [32][18], see retrieval_tc.cuh
+{
+    return cudaMemcpyFromSymbol(out, dspx::tc_trace, 32 * 18 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
 extern "C" int dspx_debug_tc_prof(long long *out16)
 {
     return cudaMemcpyFromSymbol(out16, dspx::tc_prof, 16 * sizeof(long long)) == cudaSuccess ? 0 : -1;

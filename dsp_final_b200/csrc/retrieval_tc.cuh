@@ -97,11 +97,16 @@ __global__ void __launch_bounds__(128) normalize_rows_pad32_kernel(const T *x, i
 // per-role cycle counters of CTA (0, 0): [0] mma wait acc_empty [1] mma wait full_b [2] mma issue [3] producer wait
 // [4] producer store [5] epilogue wait acc_full [6] epilogue masks [7] epilogue enqueue+drain [8] tiles [9] total
 __device__ long long tc_prof[16];
+// event trace of CTA (0, 0), tiles 64..95: [tile - 64][0] mma: acc_empty seen [1] mma: issue done [2..9] epilogue warp w: acc_full seen
+// [10..17] epilogue warp w: buffer released
+__device__ long long tc_trace[32][18];
+#define TC_TRACE(tile, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (tile) >= 64 && (tile) < 96) tc_trace[(tile) - 64][slot] = clock64(); } while (0)
 #define TC_PROF_T0() long long _pt = clock64()
 #define TC_PROF_ADD(i) do { const long long _n = clock64(); if (blockIdx.x == 0 && blockIdx.y == 0) tc_prof_local[i] += _n - _pt; _pt = _n; } while (0)
 #else
 #define TC_PROF_T0()
 #define TC_PROF_ADD(i)
+#define TC_TRACE(tile, slot)
 #endif
 
 struct TopkTcParams {
@@ -137,8 +142,13 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity)
 {
     for (uint32_t spin = 0;; spin++) {
         uint32_t ok;
+#ifdef DSPX_TC_TESTWAIT
+        asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+#else
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+#endif
         if (ok) return;
         if (spin > (1u << 28)) __trap();
     }
@@ -311,6 +321,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         // float64 row loads), so the ring is drained only when some lane has TC_FIFO_TRIGGER entries, which fills
         // the rounds.  Each lane sees its rows in increasing order.
         int f_head = 0, f_cnt = 0, wpos = 0;
+        bool thr_dirty = false;                                    // the list's k-th score or fill count changed since thr32c was formed
+#ifdef DSPX_TC_EXPERIMENT_NODRAIN
+        bool t_nodrain_skip = false;
+#endif
         int32_t *fifo = s_fifo + ql;
         auto drain = [&]() {
             while (__any_sync(0xffffffffu, f_cnt > 0)) {
@@ -345,6 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 ls[(size_t)pos * TC_QT] = s;
                 li[(size_t)pos * TC_QT] = (int32_t)row;
                 if (cnt < k) cnt++;
+                thr_dirty = true;
                 if (cnt == k) {
                     double w = INFINITY, w1 = INFINITY;           // two independent scans (even / odd entries)
                     int32_t wi = -1, wi1 = -1;
@@ -370,6 +385,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         };
         // queue the rows flagged in m (block order = row order); drains when a ring is full or 'force'
         auto enqueue = [&](uint32_t (&m)[4], int64_t tile, bool force) {
+#ifdef DSPX_TC_EXPERIMENT_NODRAIN        // timing only (results are wrong): the scan + tensor-core pipeline without re-scoring
+            if (t_nodrain_skip) { m[0] = m[1] = m[2] = m[3] = 0u; }
+#endif
+            // nothing flagged in the whole warp and no ring at its trigger: the common tile costs one vote
+            if (!force && !__any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0 || f_cnt >= TC_FIFO_TRIGGER)) return;
             for (;;) {
 #pragma unroll
                 for (int cb = 0; cb < 4; cb++) {
@@ -388,10 +408,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 if (!more) break;
             }
         };
+        // The float threshold the scan compares against.  Its float64 arithmetic (max, subtract, round down) is kept off
+        // the per-tile path: the FP64 pipe is shared by the SM and eight warps arriving together after acc_full queued on
+        // it for ~90 cycles per instruction (ncu); it is recomputed only when the list's k-th score or the shared one moved.
+        float thr32c = active ? -INFINITY : INFINITY;
+        unsigned long long genc_seen = 0;
         auto filter_threshold = [&]() -> float {
             if (!active) return INFINITY;
-            const double eff = cnt == k ? fmax(thr, gthr) : gthr;
-            return eff == -INFINITY ? -INFINITY : __double2float_rd(eff - TC_EPS);
+            if (thr_dirty || genc != genc_seen) {                  // integer tests only on the common path
+                thr_dirty = false;
+                genc_seen = genc;
+                const double eff = cnt == k ? fmax(thr, gthr) : gthr;
+                thr32c = eff == -INFINITY ? -INFINITY : __double2float_rd(eff - TC_EPS);
+            }
+            return thr32c;
         };
         if (gslot) genc = __ldcg(gslot);                           // what earlier CTAs of this query already reached
 #ifdef DSPX_TC_PROFILE
@@ -403,11 +433,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             const int64_t tile = r_begin + t * TC_ROWS;
             tc_mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
             TC_PROF_ADD(5);
+            if (lane == 0) TC_TRACE(t, 2 + warp);
             __syncwarp();                                          // tcgen05.ld is warp-collective
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (genc) gthr = tc_dec(genc);
             const uint32_t acc = lane_base + (uint32_t)(buf * 2 * TC_ROWS);
             uint32_t m[4] = {0u, 0u, 0u, 0u};
+            bool released = false;
             if (t == 0) {
                 // the list is empty: take the first tile 32 columns at a time so the threshold tightens as it fills
 #pragma unroll
@@ -417,6 +449,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 }
                 m[3] = tc_ld_mask(acc + 96, filter_threshold());
             } else {
+#ifndef DSPX_TC_LATE_RELEASE
+                // All 128 scores of the row go to registers first and the buffer is handed back to the tensor core BEFORE
+                // they are scanned: the issue thread waits for the slowest of the eight warps, and what it waited for was
+                // their scans (event trace in profiles/r02_topk_tc_pipeline.md), not the 4 x 4 KB of TMEM reads.
+                const float thr32 = filter_threshold();
+                uint32_t v0[32], v1[32], v2[32], v3[32];
+                tc_ld32_issue(acc, v0);
+                tc_ld32_issue(acc + 32, v1);
+                tc_ld32_issue(acc + 64, v2);
+                tc_ld32_issue(acc + 96, v3);
+                tc_ld_wait(v0);
+                tc_ld_wait(v1);
+                tc_ld_wait(v2);
+                tc_ld_wait(v3);
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
+                if (lane == 0) TC_TRACE(t, 10 + warp);
+                released = true;
+                m[0] = tc_mask32(v0, thr32);
+                m[1] = tc_mask32(v1, thr32);
+                m[2] = tc_mask32(v2, thr32);
+                m[3] = tc_mask32(v3, thr32);
+#else
                 const float thr32 = filter_threshold();
                 uint32_t va[32], vb[32];
                 tc_ld32_issue(acc, va);
@@ -431,12 +487,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 m[2] = tc_mask32(va, thr32);
                 tc_ld_wait(vb);
                 m[3] = tc_mask32(vb, thr32);
+#endif
             }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);        // the tensor core may overwrite this buffer now
+            if (!released) {
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);    // the tensor core may overwrite this buffer now
+                if (lane == 0) TC_TRACE(t, 10 + warp);
+            }
             if (gslot) genc = __ldcg(gslot);                       // for the next tile: in flight during the re-scoring below
             TC_PROF_ADD(6);
+#ifdef DSPX_TC_EXPERIMENT_NODRAIN
+            t_nodrain_skip = t >= 4;
+#endif
             enqueue(m, tile, t < 4 || t == n_tiles - 1);
             TC_PROF_ADD(7);
         }
@@ -516,6 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             const int s = (int)(t % TC_STAGES), buf = (int)(t & 1);
             tc_mbar_wait(&acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
             TC_PROF_ADD(0);
+            TC_TRACE(t, 0);
             tc_mbar_wait(&full_b[s], (uint32_t)((t / TC_STAGES) & 1));
             TC_PROF_ADD(1);
             asm volatile("tcgen05.fence::after_thread_sync;");
@@ -534,6 +598,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             tc_commit(&empty_b[s]);                                // smem stage free once these MMAs have read it
             tc_commit(&acc_full[buf]);                             // accumulators complete
             TC_PROF_ADD(2);
+            TC_TRACE(t, 1);
         }
 #ifdef DSPX_TC_PROFILE
         if (blockIdx.x == 0 && blockIdx.y == 0) { for (int i = 0; i < 3; i++) tc_prof[i] = tc_prof_local[i]; tc_prof[9] = clock64() - tc_start; }
