@@ -46,6 +46,10 @@ constexpr int TC_THREADS = TC_EPI_THREADS + TC_PROD_THREADS + 32;
 constexpr int TC_KPAD = 32;           // floats per row of the padded float copies (one 128-byte swizzle row)
 constexpr double TC_EPS = 8e-6;
 constexpr int TC_FIFO = 8, TC_FIFO_TRIGGER = 4;   // pending candidates per query: ring size / drain trigger
+#ifndef DSPX_TC_IDLE_CYCLES
+#define DSPX_TC_IDLE_CYCLES 3500
+#endif
+constexpr long long TC_IDLE_CYCLES = DSPX_TC_IDLE_CYCLES;   // wait on acc_full after which an epilogue warp uses the stall to re-score
 constexpr int TC_MAX_K = 28;          // the per-thread lists ([k][256] doubles + ints) share smem with the tiles
 
 // Rows scaled by 1 / (||row|| + 1e-10) in float64 (src/retrieval/retrieval.py:46-48: the division, not a multiply by
@@ -431,7 +435,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         for (int64_t t = 0; t < n_tiles; t++) {
             const int buf = (int)(t & 1);
             const int64_t tile = r_begin + t * TC_ROWS;
-            tc_mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+            // Wait for the tile.  A long wait means some other warp is re-scoring and holds the pipeline up (the issue
+            // thread needs all eight warps to hand a buffer back): re-score what this warp has pending NOW, while the
+            // time is free, instead of stalling everybody again when its own ring reaches the trigger.
+            {
+                const uint32_t parity = (uint32_t)((t >> 1) & 1);
+                bool drained = false;
+                const long long w0 = clock64();
+                for (uint32_t spin = 0;; spin++) {
+                    uint32_t ok;                                   // test_wait: try_wait would sleep through the whole stall
+                    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok) : "r"(tc_smem_u32(&acc_full[buf])), "r"(parity) : "memory");
+                    if (__all_sync(0xffffffffu, ok != 0)) break;
+                    if (spin > (1u << 28)) __trap();
+                    if (!drained && __any_sync(0xffffffffu, f_cnt > 0 && clock64() - w0 > TC_IDLE_CYCLES)) {
+                        drain();
+                        drained = true;
+                    }
+                }
+            }
             TC_PROF_ADD(5);
             if (lane == 0) TC_TRACE(t, 2 + warp);
             __syncwarp();                                          // tcgen05.ld is warp-collective
