@@ -20,16 +20,24 @@
 // all-float64 kernel's time instead of failing.
 //
 // Structure of a CTA (352 threads, one per SM), 256 queries x one database split:
-//   warps 0-7  epilogue: thread = one query.  tcgen05.ld its accumulator row (32 columns at a time, the next load
-//              in flight during the scan), compare with the thread's threshold (3-input max tree, bit mask only on
-//              a hit), release the TMEM buffer, queue the rows that pass in a per-query ring, and re-score queued
-//              rows in float64 in lock-step rounds into the thread's own unordered k-entry list in shared memory
-//              (overwrite the worst entry, rescan for the new worst; rows arrive in index order, so "strictly
-//              better than the current worst" keeps ties at the lower index; the list is ordered once at the end).
+//   warps 0-7  epilogue: thread = one query.  All 128 scores of its accumulator row go to registers (four
+//              tcgen05.ld.32x32b.x32 in flight at once), the TMEM buffer is handed back to the tensor core at once, and
+//              only then are the scores compared with the thread's float threshold (3-input max tree per 32 columns, a
+//              bit mask only when some lane of the warp has a hit; a tile without any hit costs one vote).  Rows that pass
+//              wait in a per-query ring; the WARP re-scores them together in float64 (drain: one work list over the 32
+//              rings, lane i scores item i, then every lane inserts its own rows in order into its unordered k-entry
+//              list in shared memory: overwrite the worst entry, rescan for the new worst; rows arrive in index order,
+//              so "strictly better than the current worst" keeps ties at the lower index; ordered once at the end).
+//              Re-scoring happens when a ring is full, when the warp holds 64 pending rows, or -- preferably -- while
+//              the warp would otherwise wait more than TC_IDLE_CYCLES for the next tile, i.e. while another warp's
+//              re-scoring holds the pipeline up (the issue thread needs all eight warps to release a buffer).
 //   warps 8-9  producers: database tile (128 rows x 32 floats, zero padded) from global memory, split into
 //              hi / lo, stored K-major under the 128-byte swizzle the tensor core expects; mbarrier hand-off.
 //   warp 10    one lane issues 2 x 12 tcgen05.mma (M 128, N 128, K 8) per tile into a double-buffered
 //              512-column TMEM accumulator and commits to the mbarriers of the smem stage and the buffer.
+// Measured structure (profiles/r02_topk_tc_pipeline.md): the tensor core needs 1536 cycles per tile, the TMEM read-out
+// 400-450 (320 B/clk per SM, overlapping with the MMAs: benchmarks/micro/umma_ld_overlap.cu); what the issue thread
+// waited for in round 1 were the scans and re-scoring passes of the slowest of the eight warps.
 #pragma once
 
 #include "retrieval.cuh"
@@ -45,12 +53,20 @@ constexpr int TC_EPI_THREADS = 256, TC_PROD_THREADS = 64;
 constexpr int TC_THREADS = TC_EPI_THREADS + TC_PROD_THREADS + 32;
 constexpr int TC_KPAD = 32;           // floats per row of the padded float copies (one 128-byte swizzle row)
 constexpr double TC_EPS = 8e-6;
-constexpr int TC_FIFO = 8, TC_FIFO_TRIGGER = 4;   // pending candidates per query: ring size / drain trigger
+#ifndef DSPX_TC_TRIGGER_LANE
+#define DSPX_TC_TRIGGER_LANE 8
+#endif
+#ifndef DSPX_TC_TRIGGER_WARP
+#define DSPX_TC_TRIGGER_WARP 64
+#endif
+// pending candidates per query: ring size; the warp re-scores when one ring holds TRIGGER_LANE rows or all 32 rings together
+// hold TRIGGER_WARP (one full scoring pass)
+constexpr int TC_FIFO = 8, TC_FIFO_TRIGGER = DSPX_TC_TRIGGER_LANE, TC_WARP_TRIGGER = DSPX_TC_TRIGGER_WARP;
 #ifndef DSPX_TC_IDLE_CYCLES
 #define DSPX_TC_IDLE_CYCLES 3500
 #endif
 constexpr long long TC_IDLE_CYCLES = DSPX_TC_IDLE_CYCLES;   // wait on acc_full after which an epilogue warp uses the stall to re-score
-constexpr int TC_MAX_K = 28;          // the per-thread lists ([k][256] doubles + ints) share smem with the tiles
+constexpr int TC_MAX_K = 24;          // the per-thread lists ([k][256] doubles + ints) share smem with the tiles
 
 // Rows scaled by 1 / (||row|| + 1e-10) in float64 (src/retrieval/retrieval.py:46-48: the division, not a multiply by
 // the reciprocal; the norm is the same left-to-right fma chain as normalize_rows_kernel, so out64 is bit-identical
@@ -250,7 +266,7 @@ __device__ __forceinline__ uint32_t tc_mask32(const uint32_t (&w)[32], float thr
 
 inline size_t topk_tc_smem_bytes(int k)
 {
-    return (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 4 + 128;
+    return (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 12 + 128;
 }
 
 // DIM > 0: the embedding dimension is a compile-time constant (all loads of the exact dot product in flight at
@@ -266,7 +282,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     unsigned char *b_hi = a_lo + 2 * TC_ROWS * 128;               // [TC_STAGES][128 x 128 B]
     unsigned char *b_lo = b_hi + TC_STAGES * TC_ROWS * 128;
     double *s_ls = reinterpret_cast<double *>(b_lo + TC_STAGES * TC_ROWS * 128);     // [k][256]
-    int32_t *s_li = reinterpret_cast<int32_t *>(s_ls + (size_t)p.k * TC_QT);         // [k][256]
+    double *s_sc = s_ls + (size_t)p.k * TC_QT;                                       // [TC_FIFO][256] scores of the pending rows
+    int32_t *s_li = reinterpret_cast<int32_t *>(s_sc + (size_t)TC_FIFO * TC_QT);     // [k][256]
     int32_t *s_fifo = s_li + (size_t)p.k * TC_QT;                                    // [TC_FIFO][256] pending candidate rows
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_fifo + TC_FIFO * TC_QT);         // 8-byte aligned
     uint64_t *full_b = bars, *empty_b = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
@@ -330,61 +347,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         bool t_nodrain_skip = false;
 #endif
         int32_t *fifo = s_fifo + ql;
+        // Re-scoring is shared by the warp: the pending rows of all 32 queries form one work list (prefix sum of the ring
+        // fill counts), lane i scores item i of it -- any query's row, the exact left-to-right float64 fma chain -- and
+        // leaves the score next to the ring entry; then every lane inserts its own rows in order.  A scoring pass costs
+        // the same whether 1 or 32 lanes have work (latency of the float64 row loads); with one candidate per lane and
+        // pass, ~5 pending rows per warp kept 27 lanes idle for as many passes as the fullest ring held.
         auto drain = [&]() {
-            while (__any_sync(0xffffffffu, f_cnt > 0)) {
-                if (f_cnt == 0) continue;
-                const int64_t row = fifo[(size_t)(f_head & (TC_FIFO - 1)) * TC_QT];
-                f_head++;
-                f_cnt--;
-                const double *d = p.dbn + (size_t)row * dim;
-                double s = 0.0;
-                if (DIM > 0) {
-                    double dv[DIM > 0 ? DIM : 1], qv[DIM > 0 ? DIM : 1];
+            for (;;) {
+                if (!__any_sync(0xffffffffu, f_cnt > 0)) break;
+                int pre = f_cnt;                                   // inclusive prefix sum of the fill counts
 #pragma unroll
-                    for (int c = 0; c < DIM; c++) { dv[c] = d[c]; qv[c] = qrow[c]; }
-#pragma unroll
-                    for (int c = 0; c < DIM; c++) s = fma(qv[c], dv[c], s);
-                } else {
-                    int c = 0;
-                    for (; c + 8 <= dim; c += 8) {
-                        double dv[8], qv[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) { dv[j] = d[c + j]; qv[j] = qrow[c + j]; }
-#pragma unroll
-                        for (int j = 0; j < 8; j++) s = fma(qv[j], dv[j], s);
-                    }
-                    for (; c < dim; c++) s = fma(qrow[c], d[c], s);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                    if (lane >= o) pre += v;
                 }
-                if (s < gthr) continue;                            // below another split's k-th score
-                if (cnt == k && !(s > thr)) continue;              // ties with the current worst keep the lower index
-                // the list is unordered while it runs: overwrite the worst entry, then find the new worst with k
-                // independent loads (a sorted insert would be a dependent load-compare-store chain per position)
-                const int pos = cnt < k ? cnt : wpos;
-                ls[(size_t)pos * TC_QT] = s;
-                li[(size_t)pos * TC_QT] = (int32_t)row;
-                if (cnt < k) cnt++;
-                thr_dirty = true;
-                if (cnt == k) {
-                    double w = INFINITY, w1 = INFINITY;           // two independent scans (even / odd entries)
-                    int32_t wi = -1, wi1 = -1;
-                    int wp = 0, wp1 = 0;
-                    int e = 0;
-                    for (; e + 1 < k; e += 2) {
-                        const double v = ls[(size_t)e * TC_QT], v1 = ls[(size_t)(e + 1) * TC_QT];
-                        const int32_t vi = li[(size_t)e * TC_QT], vi1 = li[(size_t)(e + 1) * TC_QT];
-                        if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
-                        if (v1 < w1 || (v1 == w1 && vi1 > wi1)) { w1 = v1; wi1 = vi1; wp1 = e + 1; }
+                const int total = __shfl_sync(0xffffffffu, pre, 31);
+                for (int w = lane; w - lane < total; w += 32) {    // warp-uniform trip count
+                    int owner = 0;                                 // first lane whose prefix exceeds w
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int pv = __shfl_sync(0xffffffffu, pre, owner + step - 1);
+                        if (pv <= w) owner += step;
                     }
-                    if (e < k) {
-                        const double v = ls[(size_t)e * TC_QT];
-                        const int32_t vi = li[(size_t)e * TC_QT];
-                        if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
+                    owner &= 31;
+                    const int o_pre = __shfl_sync(0xffffffffu, pre, owner), o_cnt = __shfl_sync(0xffffffffu, f_cnt, owner);
+                    const int o_head = __shfl_sync(0xffffffffu, f_head, owner);
+                    if (w < total) {
+                        const int slot = (o_head + (w - (o_pre - o_cnt))) & (TC_FIFO - 1);
+                        const int oq = (tid & ~31) + owner;         // the owner's query slot in this CTA
+                        const int64_t row = s_fifo[(size_t)slot * TC_QT + oq];
+                        const double *d = p.dbn + (size_t)row * dim;
+                        const double *qo = p.qn + (size_t)(q0 + oq) * dim;
+                        double sc = 0.0;
+                        if (DIM > 0) {
+                            double dv[DIM > 0 ? DIM : 1], qv[DIM > 0 ? DIM : 1];
+#pragma unroll
+                            for (int c = 0; c < DIM; c++) { dv[c] = d[c]; qv[c] = qo[c]; }
+#pragma unroll
+                            for (int c = 0; c < DIM; c++) sc = fma(qv[c], dv[c], sc);
+                        } else {
+                            int c = 0;
+                            for (; c + 8 <= dim; c += 8) {
+                                double dv[8], qv[8];
+#pragma unroll
+                                for (int j = 0; j < 8; j++) { dv[j] = d[c + j]; qv[j] = qo[c + j]; }
+#pragma unroll
+                                for (int j = 0; j < 8; j++) sc = fma(qv[j], dv[j], sc);
+                            }
+                            for (; c < dim; c++) sc = fma(qo[c], d[c], sc);
+                        }
+                        s_sc[(size_t)slot * TC_QT + oq] = sc;
                     }
-                    if (w1 < w || (w1 == w && wi1 > wi)) { w = w1; wp = wp1; }
-                    thr = w;
-                    wpos = wp;
-                    if (gslot && thr > gthr) atomicMax(gslot, tc_enc(thr));
                 }
+                __syncwarp();
+                while (f_cnt > 0) {                                // own rows, in increasing row order
+                    const int slot = f_head & (TC_FIFO - 1);
+                    const int64_t row = fifo[(size_t)slot * TC_QT];
+                    const double s = s_sc[(size_t)slot * TC_QT + ql];
+                    f_head++;
+                    f_cnt--;
+                    if (s < gthr) continue;                        // below another split's k-th score
+                    if (cnt == k && !(s > thr)) continue;          // ties with the current worst keep the lower index
+                    // the list is unordered while it runs: overwrite the worst entry, then find the new worst with k
+                    // independent loads (a sorted insert would be a dependent load-compare-store chain per position)
+                    const int pos = cnt < k ? cnt : wpos;
+                    ls[(size_t)pos * TC_QT] = s;
+                    li[(size_t)pos * TC_QT] = (int32_t)row;
+                    if (cnt < k) cnt++;
+                    thr_dirty = true;
+                    if (cnt == k) {
+                        double w = INFINITY, w1 = INFINITY;       // two independent scans (even / odd entries)
+                        int32_t wi = -1, wi1 = -1;
+                        int wp = 0, wp1 = 0;
+                        int e = 0;
+                        for (; e + 1 < k; e += 2) {
+                            const double v = ls[(size_t)e * TC_QT], v1 = ls[(size_t)(e + 1) * TC_QT];
+                            const int32_t vi = li[(size_t)e * TC_QT], vi1 = li[(size_t)(e + 1) * TC_QT];
+                            if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
+                            if (v1 < w1 || (v1 == w1 && vi1 > wi1)) { w1 = v1; wi1 = vi1; wp1 = e + 1; }
+                        }
+                        if (e < k) {
+                            const double v = ls[(size_t)e * TC_QT];
+                            const int32_t vi = li[(size_t)e * TC_QT];
+                            if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
+                        }
+                        if (w1 < w || (w1 == w && wi1 > wi)) { w = w1; wp = wp1; }
+                        thr = w;
+                        wpos = wp;
+                        if (gslot && thr > gthr) atomicMax(gslot, tc_enc(thr));
+                    }
+                }
+                __syncwarp();
             }
         };
         // queue the rows flagged in m (block order = row order); drains when a ring is full or 'force'
@@ -408,7 +461,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                     }
                 }
                 const bool more = __any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0);
-                if (more || force || __any_sync(0xffffffffu, f_cnt >= TC_FIFO_TRIGGER)) drain();
+                if (more || force || __any_sync(0xffffffffu, f_cnt >= TC_FIFO_TRIGGER) ||
+                    (int)__reduce_add_sync(0xffffffffu, (unsigned)f_cnt) >= TC_WARP_TRIGGER) drain();
                 if (!more) break;
             }
         };
