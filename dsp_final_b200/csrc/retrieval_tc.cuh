@@ -8,13 +8,21 @@
 //
 // Arithmetic: kind::tf32 keeps 10 mantissa bits of each operand (~1e-3 on a unit-vector dot product), which
 // would pass far too many pairs for tightly clustered embeddings.  Each float32 value v is therefore split
-// into hi = v with the low 13 mantissa bits cleared (exact in TF32) and lo = v - hi, and the product is
-// accumulated as A_lo B_hi + A_hi B_lo + A_hi B_hi: three K = 32 passes into the same float32 accumulator.
-// What is dropped is A_lo B_lo and the truncation of the lo operands to TF32, each below 2^-20 |q_i d_i|, i.e.
+// into hi = v with the low 13 mantissa bits cleared (11 significant bits: exact in TF32 *and* in fp16) and
+// lo = v - hi (< 2^-10 |v|), and the product is accumulated as A_lo B_hi + A_hi B_lo + A_hi B_hi into one float32
+// TMEM accumulator.  Since the last session of round 2 (TC_MIXED) only A_hi B_hi is a TF32 pass; the two cross terms
+// are ONE fp16 GEMM of K = 64, [S A_lo | A_hi] [B_hi | S B_lo]^T (kind::f16, twice the K per instruction), and the TF32
+// pass uses S A_hi, so the accumulator holds S * score with S = 2^11 -- a power of two, exact everywhere -- and the
+// scan compares against S * threshold.  S lifts the residuals into fp16's normal range (S lo < 2); fp16 rounds them to
+// 11 bits (error <= 2^-22 |v|, half of what TF32's truncation of lo to 11 bits cost), and hi is exact in fp16 down to
+// 2^-14 (below: subnormal, absolute error <= 2^-25, times S lo < 2|d_i|: < 2^-35 per component after unscaling;
+// even flushed to zero it would stay below 26 * 2^-24 = 1.5e-6 in total).  8 + 8 MMAs per tile instead of 24.
+// What is dropped is A_lo B_lo and the rounding of the lo operands, each below 2^-20 |q_i d_i|, i.e.
 // 2.9e-6 in total since sum |q_i d_i| <= 1 for unit vectors; rounding the inputs to float32 adds 1.2e-7 and twelve
 // float32 accumulator roundings at most 1.4e-6: 4.5e-6 worst case.  Measured against float64
-// (benchmarks/micro/umma_tf32.cu): 5e-7 on random and clustered unit vectors, 1.2e-6 with adversarial mantissas
-// (all 13 low bits set, all residuals of one sign).  TC_EPS = 8e-6, so every pair with s64 >= thr64 has
+// (benchmarks/micro/umma_tf32.cu, umma_f16x.cu): 5e-7 on random and clustered unit vectors, 1.2e-6 with adversarial
+// mantissas (all 13 low bits set, all residuals of one sign), the same for both schemes
+// (profiles/r02_micro_umma_f16x.txt).  TC_EPS = 8e-6, so every pair with s64 >= thr64 has
 // s_tc > thr32 = float(thr64 - eps) and is re-scored.  eps only costs extra re-scores: on tightly clustered
 // embeddings (every cosine near 1, thousands of rows within eps of the k-th score) the kernel degrades towards the
 // all-float64 kernel's time instead of failing.
@@ -32,13 +40,16 @@
 //              the warp would otherwise wait more than TC_IDLE_CYCLES for the next tile, i.e. while another warp's
 //              re-scoring holds the pipeline up (the issue thread needs all eight warps to release a buffer).
 //   warps 8-9  producers: database tile (128 rows x 32 floats, zero padded) from global memory, split into
-//              hi / lo, stored K-major under the 128-byte swizzle the tensor core expects; mbarrier hand-off.
-//   warp 10    one lane issues 2 x 12 tcgen05.mma (M 128, N 128, K 8) per tile into a double-buffered
-//              512-column TMEM accumulator and commits to the mbarriers of the smem stage and the buffer.
+//              hi (float32 tile) and the fp16 cross-term tile [hi | S lo], both K-major with 128-byte rows under the
+//              128-byte swizzle the tensor core expects; mbarrier hand-off.
+//   warp 10    one lane issues 2 x (4 kind::f16 K 16 + 4 kind::tf32 K 8) tcgen05.mma (M 128, N 128) per tile into a
+//              double-buffered 512-column TMEM accumulator and commits to the mbarriers of the smem stage and the buffer.
 // Measured structure (profiles/r02_topk_tc_pipeline.md): the tensor core needs 1536 cycles per tile, the TMEM read-out
 // 400-450 (320 B/clk per SM, overlapping with the MMAs: benchmarks/micro/umma_ld_overlap.cu); what the issue thread
 // waited for in round 1 were the scans and re-scoring passes of the slowest of the eight warps.
 #pragma once
+
+#include <cuda_fp16.h>
 
 #include "retrieval.cuh"
 
@@ -53,6 +64,11 @@ constexpr int TC_EPI_THREADS = 256, TC_PROD_THREADS = 64;
 constexpr int TC_THREADS = TC_EPI_THREADS + TC_PROD_THREADS + 32;
 constexpr int TC_KPAD = 32;           // floats per row of the padded float copies (one 128-byte swizzle row)
 constexpr double TC_EPS = 8e-6;
+#ifndef DSPX_TC_MIXED
+#define DSPX_TC_MIXED 1               // 0: the three TF32 passes of round 1 (kept for A/B timing)
+#endif
+constexpr bool TC_MIXED = DSPX_TC_MIXED != 0;
+constexpr float TC_SCALE = TC_MIXED ? 2048.f : 1.f;      // the accumulator holds TC_SCALE * score
 #ifndef DSPX_TC_TRIGGER_LANE
 #define DSPX_TC_TRIGGER_LANE 8
 #endif
@@ -186,13 +202,28 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a, uint64_
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
                  ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 
-// split a float4 into TF32-exact high parts and residuals; store both at the swizzled chunk position
-__device__ __forceinline__ void tc_store_split(unsigned char *hi_tile, unsigned char *lo_tile, int row, int chunk, float4 v)
+__device__ __forceinline__ uint2 tc_pack_half4(float a, float b, float c, float d)
+{
+    const __half2 p = __floats2half2_rn(a, b), q = __floats2half2_rn(c, d);
+    return make_uint2(*reinterpret_cast<const uint32_t *>(&p), *reinterpret_cast<const uint32_t *>(&q));
+}
+
+// Split a float4 (columns 4 * chunk ... + 3 of `row`) into TF32-exact high parts and residuals and store the operand
+// tiles at their swizzled positions.  TC_MIXED: hi_tile gets the float32 high parts (times S for the query side), x_tile
+// the fp16 row [S lo | hi] (queries) or [hi | S lo] (database): K columns 0-31 and 32-63 of the cross-term GEMM.
+// !TC_MIXED: x_tile gets the float32 residuals.
+template <bool QUERY>
+__device__ __forceinline__ void tc_store_split(unsigned char *hi_tile, unsigned char *x_tile, int row, int chunk, float4 v)
 {
     const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
     float4 h;
@@ -200,8 +231,21 @@ __device__ __forceinline__ void tc_store_split(unsigned char *hi_tile, unsigned 
     h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
     h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
     h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-    *reinterpret_cast<float4 *>(hi_tile + off) = h;
-    *reinterpret_cast<float4 *>(lo_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    if (TC_MIXED) {
+        const float s = QUERY ? TC_SCALE : 1.f;
+        *reinterpret_cast<float4 *>(hi_tile + off) = make_float4(h.x * s, h.y * s, h.z * s, h.w * s);
+        const uint2 ph = tc_pack_half4(h.x, h.y, h.z, h.w);
+        const uint2 pl = tc_pack_half4((v.x - h.x) * TC_SCALE, (v.y - h.y) * TC_SCALE, (v.z - h.z) * TC_SCALE,
+                                       (v.w - h.w) * TC_SCALE);
+        // 8 halves per 16-byte chunk: columns 4 * chunk ... are the (chunk & 1) half of chunk (chunk >> 1), + 4 for K 32-63
+        const uint32_t o0 = (uint32_t)(row * 128 + (((chunk >> 1) ^ (row & 7)) << 4) + ((chunk & 1) << 3));
+        const uint32_t o1 = (uint32_t)(row * 128 + (((4 + (chunk >> 1)) ^ (row & 7)) << 4) + ((chunk & 1) << 3));
+        *reinterpret_cast<uint2 *>(x_tile + o0) = QUERY ? pl : ph;
+        *reinterpret_cast<uint2 *>(x_tile + o1) = QUERY ? ph : pl;
+    } else {
+        *reinterpret_cast<float4 *>(hi_tile + off) = h;
+        *reinterpret_cast<float4 *>(x_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    }
 }
 
 // 32 accumulator columns of this thread's TMEM lane -> bit j set when column j passes the threshold
@@ -245,9 +289,10 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&v)[32])
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :: "memory");
 }
-// Bit j set when column j passes the threshold.  Almost every block of 32 columns is entirely below it: a max tree
-// (3-input FMNMX, log depth) decides that in 16 instructions; the mask is only built when some lane of the warp has a hit.
-__device__ __forceinline__ uint32_t tc_mask32(const uint32_t (&w)[32], float thr32)
+// Almost every block of 32 columns is entirely below the threshold: a max tree (3-input FMNMX, log depth) decides that in
+// 16 instructions per block, ONE vote covers the four blocks of a tile, and bit masks (bit j set when column j passes) are
+// only built for the blocks in which some lane of the warp has a hit.
+__device__ __forceinline__ float tc_top32(const uint32_t (&w)[32])
 {
     float mx[11];
 #pragma unroll
@@ -256,8 +301,10 @@ __device__ __forceinline__ uint32_t tc_mask32(const uint32_t (&w)[32], float thr
     mx[10] = fmaxf(__uint_as_float(w[30]), __uint_as_float(w[31]));
     const float t0 = fmaxf(fmaxf(mx[0], mx[1]), mx[2]), t1 = fmaxf(fmaxf(mx[3], mx[4]), mx[5]);
     const float t2 = fmaxf(fmaxf(mx[6], mx[7]), mx[8]), t3 = fmaxf(mx[9], mx[10]);
-    const float top = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-    if (!__any_sync(0xffffffffu, top > thr32)) return 0u;
+    return fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+}
+__device__ __forceinline__ uint32_t tc_bits32(const uint32_t (&w)[32], float thr32)
+{
     uint32_t part[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int j = 0; j < 32; j++) part[j & 3] |= (__uint_as_float(w[j]) > thr32) ? (1u << j) : 0u;
@@ -302,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     for (int c = tid; c < TC_QT * 8; c += TC_THREADS) {
         const int row = c >> 3, chunk = c & 7, a = row >> 7;
         const float4 v = *reinterpret_cast<const float4 *>(pp.qf + ((size_t)(q0 + row) * TC_KPAD + chunk * 4));
-        tc_store_split(a_hi + a * TC_ROWS * 128, a_lo + a * TC_ROWS * 128, row & 127, chunk, v);
+        tc_store_split<true>(a_hi + a * TC_ROWS * 128, a_lo + a * TC_ROWS * 128, row & 127, chunk, v);
     }
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { tc_mbar_init(&full_b[s], TC_PROD_THREADS); tc_mbar_init(&empty_b[s], 1); }
@@ -324,7 +371,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         const int ql = tid;                                        // = (warp >> 2) * 128 + (warp & 3) * 32 + lane
         const int64_t gq = q0 + ql;
         const bool active = gq < p.nq;
-        const double *qrow = p.qn + (size_t)(active ? gq : 0) * dim;
         double *ls = s_ls + ql;                                    // element e at ls[e * TC_QT]
         int32_t *li = s_li + ql;
         const int k = p.k;
@@ -440,13 +486,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 __syncwarp();
             }
         };
-        // queue the rows flagged in m (block order = row order); drains when a ring is full or 'force'
+        // queue the rows flagged in m (block order = row order); drains when a ring is full or 'force'.  Called only when
+        // some lane has a hit or 'force': every exit leaves all rings below their trigger (drain() empties them), so a tile
+        // without a hit has nothing to do here.
         auto enqueue = [&](uint32_t (&m)[4], int64_t tile, bool force) {
 #ifdef DSPX_TC_EXPERIMENT_NODRAIN        // timing only (results are wrong): the scan + tensor-core pipeline without re-scoring
             if (t_nodrain_skip) { m[0] = m[1] = m[2] = m[3] = 0u; }
 #endif
-            // nothing flagged in the whole warp and no ring at its trigger: the common tile costs one vote
-            if (!force && !__any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0 || f_cnt >= TC_FIFO_TRIGGER)) return;
             for (;;) {
 #pragma unroll
                 for (int cb = 0; cb < 4; cb++) {
@@ -477,7 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 thr_dirty = false;
                 genc_seen = genc;
                 const double eff = cnt == k ? fmax(thr, gthr) : gthr;
-                thr32c = eff == -INFINITY ? -INFINITY : __double2float_rd(eff - TC_EPS);
+                thr32c = eff == -INFINITY ? -INFINITY : __double2float_rd((eff - TC_EPS) * (double)TC_SCALE);   // power of two: exact
             }
             return thr32c;
         };
@@ -515,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             if (genc) gthr = tc_dec(genc);
             const uint32_t acc = lane_base + (uint32_t)(buf * 2 * TC_ROWS);
             uint32_t m[4] = {0u, 0u, 0u, 0u};
-            bool released = false;
+            bool released = false, any_hit = true;
             if (t == 0) {
                 // the list is empty: take the first tile 32 columns at a time so the threshold tightens as it fills
 #pragma unroll
@@ -525,7 +571,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 }
                 m[3] = tc_ld_mask(acc + 96, filter_threshold());
             } else {
-#ifndef DSPX_TC_LATE_RELEASE
                 // All 128 scores of the row go to registers first and the buffer is handed back to the tensor core BEFORE
                 // they are scanned: the issue thread waits for the slowest of the eight warps, and what it waited for was
                 // their scans (event trace in profiles/r02_topk_tc_pipeline.md), not the 4 x 4 KB of TMEM reads.
@@ -544,26 +589,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
                 if (lane == 0) TC_TRACE(t, 10 + warp);
                 released = true;
-                m[0] = tc_mask32(v0, thr32);
-                m[1] = tc_mask32(v1, thr32);
-                m[2] = tc_mask32(v2, thr32);
-                m[3] = tc_mask32(v3, thr32);
-#else
-                const float thr32 = filter_threshold();
-                uint32_t va[32], vb[32];
-                tc_ld32_issue(acc, va);
-                tc_ld_wait(va);
-                tc_ld32_issue(acc + 32, vb);
-                m[0] = tc_mask32(va, thr32);
-                tc_ld_wait(vb);
-                tc_ld32_issue(acc + 64, va);
-                m[1] = tc_mask32(vb, thr32);
-                tc_ld_wait(va);
-                tc_ld32_issue(acc + 96, vb);
-                m[2] = tc_mask32(va, thr32);
-                tc_ld_wait(vb);
-                m[3] = tc_mask32(vb, thr32);
-#endif
+                const float t0 = tc_top32(v0), t1 = tc_top32(v1), t2 = tc_top32(v2), t3 = tc_top32(v3);
+                any_hit = __any_sync(0xffffffffu, fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) > thr32);
+                if (any_hit) {
+                    if (__any_sync(0xffffffffu, t0 > thr32)) m[0] = tc_bits32(v0, thr32);
+                    if (__any_sync(0xffffffffu, t1 > thr32)) m[1] = tc_bits32(v1, thr32);
+                    if (__any_sync(0xffffffffu, t2 > thr32)) m[2] = tc_bits32(v2, thr32);
+                    if (__any_sync(0xffffffffu, t3 > thr32)) m[3] = tc_bits32(v3, thr32);
+                }
             }
             if (!released) {
                 asm volatile("tcgen05.fence::before_thread_sync;");
@@ -576,7 +609,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
 #ifdef DSPX_TC_EXPERIMENT_NODRAIN
             t_nodrain_skip = t >= 4;
 #endif
-            enqueue(m, tile, t < 4 || t == n_tiles - 1);
+            {
+                const bool force = t < 4 || t == n_tiles - 1;
+                if (any_hit || force) enqueue(m, tile, force);
+            }
             TC_PROF_ADD(7);
         }
 #ifdef DSPX_TC_PROFILE
@@ -633,7 +669,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
 #pragma unroll
             for (int i = 0; i < PER; i++) {
                 const int c = ptid + i * TC_PROD_THREADS;
-                tc_store_split(hi, lo, c >> 3, c & 7, v[i]);
+                tc_store_split<false>(hi, lo, c >> 3, c & 7, v[i]);
             }
             asm volatile("fence.proxy.async.shared::cta;");
             tc_mbar_arrive(&full_b[s]);
@@ -646,6 +682,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     } else if (lane == 0) {
         // ===== tensor-core issue: one thread =====
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc16 = (1u << 4) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32
+        (void)idesc16;
 #ifdef DSPX_TC_PROFILE
         long long tc_prof_local[16] = {0};
         const long long tc_start = clock64();
@@ -664,10 +702,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             for (int a = 0; a < 2; a++) {
                 const uint64_t ah = tc_desc(a_hi + a * TC_ROWS * 128), al = tc_desc(a_lo + a * TC_ROWS * 128);
                 const uint32_t d = tmem + (uint32_t)(buf * 2 * TC_ROWS + a * TC_ROWS);
+                if (TC_MIXED) {
+                    // both cross terms as one fp16 GEMM of K = 64 (4 x K 16; 32 bytes per step like TF32's K 8), then S A_hi B_hi
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, al + 2 * kk, bh + 2 * kk, idesc, kk > 0);     // small terms first
+                    for (int kk = 0; kk < 4; kk++) tc_mma_f16(d, al + 2 * kk, bl + 2 * kk, idesc16, kk > 0);   // small terms first
+                } else {
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                    for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, al + 2 * kk, bh + 2 * kk, idesc, kk > 0);    // small terms first
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                }
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
             }

@@ -1,0 +1,34 @@
+#!/usr/bin/env bash
+# One-GPU A/B of the retrieval filter's mixed TF32 + fp16 split (last session of round 2):
+#   gpurun -- 'bash tools/capture_r02g.sh ab'      error micro-benchmark, retrieval GPU tests, retr_quick on three libraries
+#   gpurun -- 'bash tools/capture_r02g.sh final'   whole GPU suite, bench lines, launch list, ncu of the retrieval kernel
+# The A/B libraries live in gpurun_scratch/ (git-ignored, travels with the snapshot): libdspx_head.so = the previous
+# commit, libdspx_mixed_4vote.so = mixed split with the per-block votes, libdspx_prof.so = -DDSPX_TC_PROFILE.
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+PART=${1:-ab}
+export LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:${LD_LIBRARY_PATH:-}
+BENCH_ARGS="--steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --stft-steps 2 --retrieval-steps 1"
+if [ "$PART" = ab ]; then
+timeout 60 benchmarks/micro/umma_f16x > $OUT/r02g_umma_f16x.txt 2>&1; echo "umma_f16x rc=$?"; grep -c "max err" $OUT/r02g_umma_f16x.txt
+timeout 600 python -m pytest tests -m gpu -x -q -k "retrieval or topk or sharded or pipeline or embed" > $OUT/r02g_gputest_retr.log 2>&1; echo "retrieval gpu tests rc=$?"; tail -2 $OUT/r02g_gputest_retr.log
+timeout 300 python benchmarks/retr_quick.py > $OUT/r02g_retr_quick_new.txt 2>&1; echo "quick new rc=$?"; cat $OUT/r02g_retr_quick_new.txt
+for lib in head mixed_4vote; do
+  if [ -f gpurun_scratch/libdspx_$lib.so ]; then
+    DSPX_LIBRARY=$PWD/gpurun_scratch/libdspx_$lib.so timeout 300 python benchmarks/retr_quick.py > $OUT/r02g_retr_quick_$lib.txt 2>&1; echo "quick $lib rc=$?"; cat $OUT/r02g_retr_quick_$lib.txt
+  fi
+done
+for sp in 5 9 11 13; do DSPX_TOPK_SPLITS=$sp timeout 120 python benchmarks/retr_time.py 2>&1 | tail -1 | sed "s/^/splits $sp: /" >> $OUT/r02g_retr_splits.txt; done; cat $OUT/r02g_retr_splits.txt
+if [ -f gpurun_scratch/libdspx_prof.so ]; then
+  DSPX_LIBRARY=$PWD/gpurun_scratch/libdspx_prof.so timeout 300 python benchmarks/retr_tc_roles_steady.py > $OUT/r02g_roles_steady.txt 2>&1; echo "roles rc=$?"; cat $OUT/r02g_roles_steady.txt
+fi
+else
+python -m pytest tests -m gpu -x -q > $OUT/r02g_gputest.log 2>&1; echo "gpu tests rc=$?"; tail -2 $OUT/r02g_gputest.log
+python bench.py > $OUT/r02g_bench_1gpu.log 2> $OUT/r02g_bench_1gpu.err; echo "bench rc=$?"
+python bench.py --impl reference > $OUT/r02g_bench_reference.log 2> $OUT/r02g_bench_reference.err; echo "reference arm rc=$?"
+python bench.py $BENCH_ARGS > $OUT/r02g_bench_plain.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/r02g_launches_raw.csv python bench.py $BENCH_ARGS > $OUT/r02g_ncu_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:cosine_topk_tc_kernel -c 1 -o $OUT/r02g_topk_tc -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_topk.log 2>&1
+fi
+ls -la $OUT | grep r02g
