@@ -3,7 +3,11 @@
 //     + [S A_lo | A_hi] [B_hi | S B_lo]^T   kind::f16, K = 64: both cross terms as ONE fp16 GEMM (S = 2^11 keeps the
 //                                            residuals in fp16's normal range; hi is exact in fp16 above 2^-14)
 // into the same float32 TMEM accumulator: 8 + 8 MMAs per 256 x 128 tile instead of the 24 of the three TF32 passes.
-// SPLIT = 1 is the old three-pass scheme, SPLIT = 2 the mixed one; both are compared with float64 on the host.
+// SPLIT = 1 is the old three-pass scheme, SPLIT = 2 the mixed one, SPLIT = 3 the final all-fp16 one: ONE operand format
+// [S hi | S lo] (64 halves = one 128-byte row) for both sides, the three terms are K slices of the same rows
+// (A[32..63] x B[0..31], A[0..31] x B[32..63], A[0..31] x B[0..31]; accumulator = S^2 * score), 6 MMAs of K = 16 per
+// 128 x 128 tile; the B tile is written to global memory in its swizzled image and fetched with cp.async.bulk, as the
+// kernel does.  All are compared with float64 on the host.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_f16x umma_f16x.cu
 #include <cstdint>
 #include <cstdio>
@@ -60,7 +64,7 @@ __device__ __forceinline__ uint32_t swz_h(int row, int col)   // byte offset of 
 }
 
 template <int SPLIT>
-__global__ void __launch_bounds__(128) k(const float *A, const float *B, float *C, int *status)
+__global__ void __launch_bounds__(128) k(const float *A, const float *B, float *C, int *status, unsigned char *scratch)
 {
     extern __shared__ __align__(1024) unsigned char raw[];
     unsigned char *base = (unsigned char *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -77,6 +81,10 @@ __global__ void __launch_bounds__(128) k(const float *A, const float *B, float *
             *(__half *)(sAl + swz_h(r, c)) = __float2half_rn((v - hi) * XS);
             *(__half *)(sAl + swz_h(r, 32 + c)) = __float2half_rn(hi);
         }
+        if (SPLIT == 3) {
+            *(__half *)(sAl + swz_h(r, c)) = __float2half_rn(hi * XS);
+            *(__half *)(sAl + swz_h(r, 32 + c)) = __float2half_rn((v - hi) * XS);
+        }
     }
     for (int e = tid; e < N * K; e += 128) {
         const float v = B[e], hi = SPLIT ? __uint_as_float(__float_as_uint(v) & 0xffffe000u) : v;
@@ -86,6 +94,23 @@ __global__ void __launch_bounds__(128) k(const float *A, const float *B, float *
         if (SPLIT == 2) {
             *(__half *)(sBl + swz_h(r, c)) = __float2half_rn(hi);
             *(__half *)(sBl + swz_h(r, 32 + c)) = __float2half_rn((v - hi) * XS);
+        }
+        if (SPLIT == 3) {                                      // image in global memory; the bulk copy below brings it in
+            *(__half *)(scratch + swz_h(r, c)) = __float2half_rn(hi * XS);
+            *(__half *)(scratch + swz_h(r, 32 + c)) = __float2half_rn((v - hi) * XS);
+        }
+    }
+    __shared__ uint64_t bar_b;
+    if (SPLIT == 3) {
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");       // generic-proxy global writes -> the bulk copy's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            mbar_init(&bar_b, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_b)), "r"(N * 128) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sBl)), "l"(scratch), "r"(N * 128), "r"(smem_u32(&bar_b)) : "memory");
         }
     }
     if (tid == 0) {
@@ -103,7 +128,18 @@ __global__ void __launch_bounds__(128) k(const float *A, const float *B, float *
     const uint32_t tmem = slot;
     if (tid == 0) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-        if (SPLIT == 2) {
+        if (SPLIT == 3) {
+            if (!mbar_wait(&bar_b, 0)) *status = 2;
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t idesc16 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // f16 x f16 -> f32
+            const uint64_t ad = make_desc(sAl), bd = make_desc(sBl);
+            const uint64_t as[6] = {ad + 4, ad + 6, ad, ad + 2, ad, ad + 2}, bs[6] = {bd, bd + 2, bd + 4, bd + 6, bd, bd + 2};
+            for (int i = 0; i < 6; i++) {
+                const uint32_t acc = i > 0;
+                asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                             ::"r"(tmem), "l"(as[i]), "l"(bs[i]), "r"(idesc16), "r"(acc));
+            }
+        } else if (SPLIT == 2) {
             const uint32_t idesc16 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // f16 x f16 -> f32
             const uint64_t ax = make_desc(sAl), bx = make_desc(sBl), ah = make_desc(sA), bh = make_desc(sB);
             for (int kk = 0; kk < 4; kk++) {                   // small terms first
@@ -143,7 +179,7 @@ __global__ void __launch_bounds__(128) k(const float *A, const float *B, float *
                            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr + c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            for (int j = 0; j < 32; j++) C[(size_t)(32 * warp + lane) * N + c0 + j] = __uint_as_float(v[j]) * (SPLIT == 2 ? 1.f / XS : 1.f);
+            for (int j = 0; j < 32; j++) C[(size_t)(32 * warp + lane) * N + c0 + j] = __uint_as_float(v[j]) * (SPLIT == 3 ? 1.f / (XS * XS) : SPLIT == 2 ? 1.f / XS : 1.f);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -156,26 +192,32 @@ static int run(int split, const std::vector<float> &A, const std::vector<float> 
     std::vector<float> C(M * N, -1.f);
     float *dA, *dB, *dC;
     int *dS, st = 0;
+    unsigned char *dX;
+    cudaMalloc(&dX, N * 128);
+    cudaMemset(dX, 0, N * 128);
     cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dC, C.size() * 4); cudaMalloc(&dS, 4);
     cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
     cudaMemset(dS, 0, 4);
     const size_t smem = 2 * (M + N) * 128 + 1024;
-    if (split == 2) {
+    if (split == 3) {
+        cudaFuncSetAttribute(k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<3><<<1, 128, smem>>>(dA, dB, dC, dS, dX);
+    } else if (split == 2) {
         cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<2><<<1, 128, smem>>>(dA, dB, dC, dS);
+        k<2><<<1, 128, smem>>>(dA, dB, dC, dS, dX);
     } else if (split == 1) {
         cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<1><<<1, 128, smem>>>(dA, dB, dC, dS);
+        k<1><<<1, 128, smem>>>(dA, dB, dC, dS, dX);
     } else {
         cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<0><<<1, 128, smem>>>(dA, dB, dC, dS);
+        k<0><<<1, 128, smem>>>(dA, dB, dC, dS, dX);
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf("split=%d launch: %s\n", split, cudaGetErrorString(e));
     cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
-    printf("status (1 = mbarrier timeout): %d\n", st);
+    printf("status (1 = mbarrier timeout, 2 = bulk copy timeout): %d\n", st);
     int bad = 0;
     double maxerr = 0;
     for (int i = 0; i < M; i++)
@@ -187,7 +229,7 @@ static int run(int split, const std::vector<float> &A, const std::vector<float> 
             if (err > tol) { if (bad < 5) printf("mismatch C[%d][%d] = %g want %g\n", i, j, C[i * N + j], ref); bad++; }
         }
     printf("mismatches: %d of %d, max err %g (tolerance %g)\n", bad, M * N, maxerr, tol);
-    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS); cudaFree(dX);
     return bad != 0 || st != 0 || e != cudaSuccess;
 }
 
@@ -199,6 +241,7 @@ int main()
     for (auto &v : B) v = (float)(rand() % 33 - 16) / 8.f;
     int rc = run(0, A, B, 1e-5);
     rc |= run(2, A, B, 1e-5);
+    rc |= run(3, A, B, 1e-5);
     // unit vectors of dimension 26 (zero padded to 32), several magnitudes of clustering
     for (int trial = 0; trial < 3; trial++) {
         const double spread = trial == 0 ? 1.0 : (trial == 1 ? 0.05 : 0.001);
@@ -214,6 +257,7 @@ int main()
         printf("-- unit vectors, spread %g\n", spread);
         rc |= run(1, A, B, 2e-6);
         rc |= run(2, A, B, 2e-6);
+        rc |= run(3, A, B, 2e-6);
     }
     // wide dynamic range: a few large components and many tiny ones (down to 1e-9 of the norm): the small high parts and
     // scaled residuals fall into fp16's subnormal range (or flush to zero) -- the bound in retrieval_tc.cuh covers both
@@ -235,6 +279,7 @@ int main()
         printf("-- wide dynamic range, components down to 1e-%d of the largest\n", 3 + 3 * trial);
         rc |= run(1, A, B, 2e-6);
         rc |= run(2, A, B, 2e-6);
+        rc |= run(3, A, B, 2e-6);
     }
     // adversarial mantissas: every value has its 13 low bits set (largest possible residual, all of one sign)
     for (int trial = 0; trial < 2; trial++) {
@@ -257,6 +302,7 @@ int main()
         printf("-- adversarial low mantissa bits, trial %d\n", trial);
         rc |= run(1, A, B, 8e-6);
         rc |= run(2, A, B, 8e-6);
+        rc |= run(3, A, B, 8e-6);
     }
     printf("rc=%d\n", rc);
     return rc;

@@ -911,7 +911,7 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     ws += align256(dbf_bytes);
     unsigned long long *shared_thr = reinterpret_cast<unsigned long long *>(ws);
     // Filter kernels (single-chunk dimensions, lists that fit beside the tiles), all with exact float64 re-scoring:
-    // tensor-core TF32 filter, else packed-FP32 filter, else the all-float64 kernel.  DSPX_TOPK = tc | f32 | f64 forces one.
+    // tensor-core (split fp16) filter, else packed-FP32 filter, else the all-float64 kernel.  DSPX_TOPK = tc | f32 | f64 forces one.
     const TopkKnobs &knobs = topk_knobs();
     const char *force = knobs.force;
     const bool want_f64 = knobs.f64 || (force && !strcmp(force, "f64"));
@@ -921,15 +921,16 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     const bool prefilter = !want_f64 && !use_tc && f32_ok;
 
     if (use_tc) {
-        // the kernel writes the zero padding too (columns >= dim, rows up to the tile multiple): no memset pass
+        // fp16 operand images (128 bytes per row, same size as the float copies of the other filter); the kernel writes the
+        // zero padding too (columns >= dim, rows up to the tile multiple): no memset pass
         const int64_t nq_pad = (nq + TC_QT - 1) / TC_QT * TC_QT, ndb_pad = (ndb + TK_ROWS - 1) / TK_ROWS * TK_ROWS;
         const unsigned gq = (unsigned)((nq_pad + NR_ROWS - 1) / NR_ROWS), gd = (unsigned)((ndb_pad + NR_ROWS - 1) / NR_ROWS);
         if (dtype == DSPX_DTYPE_F32) {
-            normalize_rows_pad32_kernel<float><<<gq, 128, 0, st>>>((const float *)q_dev, nq, nq_pad, dim, qn, qf_t);
-            normalize_rows_pad32_kernel<float><<<gd, 128, 0, st>>>((const float *)db_dev, ndb, ndb_pad, dim, dbn, dbf_t);
+            normalize_rows_split16_kernel<float><<<gq, 128, 0, st>>>((const float *)q_dev, nq, nq_pad, dim, qn, (unsigned char *)qf_t);
+            normalize_rows_split16_kernel<float><<<gd, 128, 0, st>>>((const float *)db_dev, ndb, ndb_pad, dim, dbn, (unsigned char *)dbf_t);
         } else {
-            normalize_rows_pad32_kernel<double><<<gq, 128, 0, st>>>((const double *)q_dev, nq, nq_pad, dim, qn, qf_t);
-            normalize_rows_pad32_kernel<double><<<gd, 128, 0, st>>>((const double *)db_dev, ndb, ndb_pad, dim, dbn, dbf_t);
+            normalize_rows_split16_kernel<double><<<gq, 128, 0, st>>>((const double *)q_dev, nq, nq_pad, dim, qn, (unsigned char *)qf_t);
+            normalize_rows_split16_kernel<double><<<gd, 128, 0, st>>>((const double *)db_dev, ndb, ndb_pad, dim, dbn, (unsigned char *)dbf_t);
         }
     } else
     if (prefilter) {
@@ -990,8 +991,8 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
         if (use_tc) {
             TopkTcParams cp{};
             cp.base = tp;
-            cp.qf = qf_t;
-            cp.dbf = dbf_t;
+            cp.qx = reinterpret_cast<const unsigned char *>(qf_t);
+            cp.dbx = reinterpret_cast<const unsigned char *>(dbf_t);
             cp.shared_thr = tp.n_splits > 1 ? shared_thr : nullptr;
 #ifdef DSPX_TC_PROFILE                  // profiling builds only: DSPX_EXPERIMENT_KEEP_THR=1 keeps the thresholds of the previous call (steady-state per-role cycles)
             if (cp.shared_thr && !getenv("DSPX_EXPERIMENT_KEEP_THR"))

@@ -6,32 +6,37 @@
 // current k-th score are produced by the 5th-generation tensor cores; the few pairs that pass are re-scored
 // exactly in float64.  Replaces the argsort over the dense matrix of src/retrieval/retrieval.py:25-49.
 //
-// Arithmetic: kind::tf32 keeps 10 mantissa bits of each operand (~1e-3 on a unit-vector dot product), which
-// would pass far too many pairs for tightly clustered embeddings.  Each float32 value v is therefore split
-// into hi = v with the low 13 mantissa bits cleared (11 significant bits: exact in TF32 *and* in fp16) and
-// lo = v - hi (< 2^-10 |v|), and the product is accumulated as A_lo B_hi + A_hi B_lo + A_hi B_hi into one float32
-// TMEM accumulator.  Since the last session of round 2 (TC_MIXED) only A_hi B_hi is a TF32 pass; the two cross terms
-// are ONE fp16 GEMM of K = 64, [S A_lo | A_hi] [B_hi | S B_lo]^T (kind::f16, twice the K per instruction), and the TF32
-// pass uses S A_hi, so the accumulator holds S * score with S = 2^11 -- a power of two, exact everywhere -- and the
-// scan compares against S * threshold.  S lifts the residuals into fp16's normal range (S lo < 2); fp16 rounds them to
-// 11 bits (error <= 2^-22 |v|, half of what TF32's truncation of lo to 11 bits cost), and hi is exact in fp16 down to
-// 2^-14 (below: subnormal, absolute error <= 2^-25, times S lo < 2|d_i|: < 2^-35 per component after unscaling;
-// even flushed to zero it would stay below 26 * 2^-24 = 1.5e-6 in total).  8 + 8 MMAs per tile instead of 24.
-// What is dropped is A_lo B_lo and the rounding of the lo operands, each below 2^-20 |q_i d_i|, i.e.
-// 2.9e-6 in total since sum |q_i d_i| <= 1 for unit vectors; rounding the inputs to float32 adds 1.2e-7 and twelve
-// float32 accumulator roundings at most 1.4e-6: 4.5e-6 worst case.  Measured against float64
-// (benchmarks/micro/umma_tf32.cu, umma_f16x.cu): 5e-7 on random and clustered unit vectors, 1.2e-6 with adversarial
-// mantissas (all 13 low bits set, all residuals of one sign), the same for both schemes
-// (profiles/r02_micro_umma_f16x.txt).  TC_EPS = 8e-6, so every pair with s64 >= thr64 has
-// s_tc > thr32 = float(thr64 - eps) and is re-scored.  eps only costs extra re-scores: on tightly clustered
-// embeddings (every cosine near 1, thousands of rows within eps of the k-th score) the kernel degrades towards the
-// all-float64 kernel's time instead of failing.
+// Arithmetic.  A single reduced-precision pass (TF32: 10 mantissa bits, ~1e-3 on a unit-vector dot product) would pass far
+// too many pairs for tightly clustered embeddings.  Each float32 value v is therefore split into hi = v with the low 13
+// mantissa bits cleared (11 significant bits) and lo = v - hi (< 2^-10 |v|), and the filter accumulates
+// A_lo B_hi + A_hi B_lo + A_hi B_hi into one float32 TMEM accumulator.  Round 1 ran these as three TF32 passes (24 MMAs of
+// K = 8 per 256 x 128 tile, 1536 tensor cycles).  hi has 11 significant bits: it is exact in fp16 as well, and so are all
+// products (22 bits into a float32 accumulator), so since the last session of round 2 ALL THREE terms are kind::f16 MMAs
+// (K = 16 per instruction: 12 MMAs, 768 cycles per tile) on ONE operand format for queries and database alike: a 128-byte row
+// of 64 halves [S hi(0..31) | S lo(0..31)] with S = 2^11 (a power of two: exact).  S lifts the operands into fp16's normal
+// range (S hi <= 2048, S lo < 2; a value only turns subnormal below 2^-25 of the norm, where even flushing it to zero costs
+// < 1.5e-7 in total) and the accumulator holds S^2 * score; the scan compares against S^2 * threshold.  The three terms are
+// K slices of the same two rows:  A[32..63] x B[0..31]  (lo hi),  A[0..31] x B[32..63]  (hi lo),  A[0..31] x B[0..31]  (hi hi).
+// fp16 rounds lo to 11 bits (error <= 2^-22 |v|; TF32 truncated it: 2^-21).  What is dropped is A_lo B_lo and that rounding,
+// each below 2^-20 |q_i d_i|, i.e. 2.9e-6 in total since sum |q_i d_i| <= 1 for unit vectors; rounding the inputs to float32
+// adds 1.2e-7 and the float32 accumulation at most 1.4e-6: 4.5e-6 worst case.  Measured against float64
+// (benchmarks/micro/umma_f16x.cu, profiles/r02_micro_umma_f16x.txt): <= 6.5e-7 on random, clustered and wide-dynamic-range
+// unit vectors and with adversarial mantissas (all 13 low bits set, all residuals of one sign; three TF32 passes: 1.2e-6).
+// TC_EPS = 8e-6, so every pair with s64 >= thr64 has s_tc > thr32 = float(thr64 - eps) and is re-scored.  eps only costs
+// extra re-scores: on tightly clustered embeddings (every cosine near 1, thousands of rows within eps of the k-th score) the
+// kernel degrades towards the all-float64 kernel's time instead of failing.
 //
-// Structure of a CTA (352 threads, one per SM), 256 queries x one database split:
+// The operand rows are written ONCE, by the normalisation kernel, already in the 128-byte-swizzled K-major tile image the
+// tensor core reads (16 KB per 128 rows), so a database tile reaches shared memory as one bulk copy (cp.async.bulk, the TMA
+// engine's 1-D form, completion on an mbarrier) issued by a single thread.  Until then two producer warps re-split every tile
+// for every query tile with ordinary loads and stores (~1100 cycles per tile, as long as the MMAs themselves) and the epilogue
+// warps that shared their schedulers were the laggards the issue thread waited for (profiles/r02_topk_tc_mixed_ab.txt).
+//
+// Structure of a CTA (320 threads, one per SM), 256 queries x one database split:
 //   warps 0-7  epilogue: thread = one query.  All 128 scores of its accumulator row go to registers (four
 //              tcgen05.ld.32x32b.x32 in flight at once), the TMEM buffer is handed back to the tensor core at once, and
-//              only then are the scores compared with the thread's float threshold (3-input max tree per 32 columns, a
-//              bit mask only when some lane of the warp has a hit; a tile without any hit costs one vote).  Rows that pass
+//              only then are the scores compared with the thread's float threshold (3-input max tree per 32 columns, ONE vote
+//              per tile, bit masks only for blocks in which some lane of the warp has a hit).  Rows that pass
 //              wait in a per-query ring; the WARP re-scores them together in float64 (drain: one work list over the 32
 //              rings, lane i scores item i, then every lane inserts its own rows in order into its unordered k-entry
 //              list in shared memory: overwrite the worst entry, rescan for the new worst; rows arrive in index order,
@@ -39,11 +44,10 @@
 //              Re-scoring happens when a ring is full, when the warp holds 64 pending rows, or -- preferably -- while
 //              the warp would otherwise wait more than TC_IDLE_CYCLES for the next tile, i.e. while another warp's
 //              re-scoring holds the pipeline up (the issue thread needs all eight warps to release a buffer).
-//   warps 8-9  producers: database tile (128 rows x 32 floats, zero padded) from global memory, split into
-//              hi (float32 tile) and the fp16 cross-term tile [hi | S lo], both K-major with 128-byte rows under the
-//              128-byte swizzle the tensor core expects; mbarrier hand-off.
-//   warp 10    one lane issues 2 x (4 kind::f16 K 16 + 4 kind::tf32 K 8) tcgen05.mma (M 128, N 128) per tile into a
-//              double-buffered 512-column TMEM accumulator and commits to the mbarriers of the smem stage and the buffer.
+//   warp 8     one lane: bulk copies of the query tiles (once) and of the database tiles into a 4-stage ring; mbarrier
+//              expect_tx / complete_tx hand-off to the issue thread.
+//   warp 9     one lane issues 2 x 6 tcgen05.mma kind::f16 (M 128, N 128, K 16) per tile into a double-buffered
+//              512-column TMEM accumulator and commits to the mbarriers of the smem stage and the buffer.
 // Measured structure (profiles/r02_topk_tc_pipeline.md): the tensor core needs 1536 cycles per tile, the TMEM read-out
 // 400-450 (320 B/clk per SM, overlapping with the MMAs: benchmarks/micro/umma_ld_overlap.cu); what the issue thread
 // waited for in round 1 were the scans and re-scoring passes of the slowest of the eight warps.
@@ -59,16 +63,14 @@ namespace dspx {
 
 constexpr int TC_QT = 256;            // queries per CTA: two 128-row A tiles
 constexpr int TC_ROWS = 128;          // database rows per tile (UMMA N)
-constexpr int TC_STAGES = 2;
-constexpr int TC_EPI_THREADS = 256, TC_PROD_THREADS = 64;
-constexpr int TC_THREADS = TC_EPI_THREADS + TC_PROD_THREADS + 32;
-constexpr int TC_KPAD = 32;           // floats per row of the padded float copies (one 128-byte swizzle row)
+constexpr int TC_STAGES = 4;          // database tiles in flight (16 KB each)
+constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_THREADS = TC_EPI_THREADS + 32 + 32;      // + bulk-copy warp + tensor-core issue warp
+constexpr int TC_KPAD = 32;           // padded embedding dimension: 32 hi + 32 lo halves = one 128-byte swizzle row
+constexpr int TC_TILE_BYTES = 128 * 128;                  // operand image of 128 rows
 constexpr double TC_EPS = 8e-6;
-#ifndef DSPX_TC_MIXED
-#define DSPX_TC_MIXED 1               // 0: the three TF32 passes of round 1 (kept for A/B timing)
-#endif
-constexpr bool TC_MIXED = DSPX_TC_MIXED != 0;
-constexpr float TC_SCALE = TC_MIXED ? 2048.f : 1.f;      // the accumulator holds TC_SCALE * score
+constexpr float TC_S = 2048.f;                            // operand scale S = 2^11
+constexpr float TC_SCALE = TC_S * TC_S;                   // the accumulator holds S^2 * score
 #ifndef DSPX_TC_TRIGGER_LANE
 #define DSPX_TC_TRIGGER_LANE 8
 #endif
@@ -86,14 +88,17 @@ constexpr int TC_MAX_K = 24;          // the per-thread lists ([k][256] doubles 
 
 // Rows scaled by 1 / (||row|| + 1e-10) in float64 (src/retrieval/retrieval.py:46-48: the division, not a multiply by
 // the reciprocal; the norm is the same left-to-right fma chain as normalize_rows_kernel, so out64 is bit-identical
-// to it) plus the zero-padded float32 copy [n_pad][32] the tensor-core filter reads.  A CTA owns NR_ROWS consecutive
-// rows: they are one contiguous span of the input and of both outputs, so every global access is coalesced (the
-// round-1 kernel had one thread walk one row: 26 strided stores per thread, 9x the HBM time of the copy).
+// to it) plus the fp16 operand image the tensor-core filter reads: per 128 rows a 16 KB tile, row r at r * 128 bytes, its
+// eight 16-byte chunks (chunks 0-3: S hi of columns 0-31, chunks 4-7: S lo; zero beyond dim and beyond n) at position
+// chunk ^ (r & 7) -- the 128-byte swizzle of a K-major operand, so the kernel's bulk copy is a plain memcpy of the tile.
+// A CTA owns NR_ROWS consecutive rows: they are one contiguous span of the input and of both outputs, so every global
+// access is coalesced (the round-1 kernel had one thread walk one row: 26 strided stores per thread, 9x the HBM time of
+// the copy).
 constexpr int NR_ROWS = 64;
 
 template <typename T>
-__global__ void __launch_bounds__(128) normalize_rows_pad32_kernel(const T *x, int64_t n, int64_t n_pad, int dim,
-                                                                  double *out64, float *out32)
+__global__ void __launch_bounds__(128) normalize_rows_split16_kernel(const T *x, int64_t n, int64_t n_pad, int dim,
+                                                                    double *out64, unsigned char *out16)
 {
     __shared__ T s_in[NR_ROWS * TC_KPAD];
     __shared__ float s_f32[NR_ROWS * TC_KPAD];
@@ -124,9 +129,22 @@ __global__ void __launch_bounds__(128) normalize_rows_pad32_kernel(const T *x, i
     }
     __syncthreads();
     const int64_t pad_rows = (n_pad - r0) < NR_ROWS ? (n_pad - r0) : NR_ROWS;
-    float4 *d32 = reinterpret_cast<float4 *>(out32 + (size_t)r0 * TC_KPAD);
-    const float4 *s32 = reinterpret_cast<const float4 *>(s_f32);
-    for (int e = tid; e < pad_rows * (TC_KPAD / 4); e += 128) d32[e] = s32[e];
+    // r0 is a multiple of 64: the CTA's rows lie inside one 128-row tile
+    unsigned char *tile = out16 + (size_t)(r0 >> 7) * TC_TILE_BYTES;
+    for (int e = tid; e < pad_rows * 8; e += 128) {
+        const int r = e >> 3, chunk = e & 7, rt = (int)((r0 + r) & 127);
+        const float *v = s_f32 + r * TC_KPAD + (chunk & 3) * 8;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float a = v[2 * j], b = v[2 * j + 1];
+            const float ah = __uint_as_float(__float_as_uint(a) & 0xffffe000u), bh = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
+            const __half2 h = chunk < 4 ? __floats2half2_rn(ah * TC_S, bh * TC_S)                 // exact: 11 significant bits
+                                        : __floats2half2_rn((a - ah) * TC_S, (b - bh) * TC_S);   // residual, rounded to 11 bits
+            w[j] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        *reinterpret_cast<uint4 *>(tile + rt * 128 + ((chunk ^ (rt & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
 #ifdef DSPX_TC_PROFILE
@@ -147,8 +165,8 @@ __device__ long long tc_trace[32][18];
 
 struct TopkTcParams {
     TopkParams base;
-    const float *qf;        // [ceil(nq / 256) * 256][32], zero padded
-    const float *dbf;       // [ceil(ndb / 128) * 128][32], zero padded
+    const unsigned char *qx;    // fp16 operand tiles of the queries: [ceil(nq / 256) * 2][16 KB] (normalize_rows_split16_kernel)
+    const unsigned char *dbx;   // fp16 operand tiles of the database: [ceil(ndb / 128)][16 KB]
     unsigned long long *shared_thr;   // [nq] order-encoded k-th scores shared by the splits of a query (null: one split)
 };
 
@@ -197,11 +215,6 @@ __device__ __forceinline__ uint64_t tc_desc(const void *tile)
            ((uint64_t)2 << 61);
 }
 
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
-                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
@@ -212,40 +225,15 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ uint2 tc_pack_half4(float a, float b, float c, float d)
+// mbarrier transaction count + the TMA engine's 1-D bulk copy global -> shared (completes on the barrier)
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
-    const __half2 p = __floats2half2_rn(a, b), q = __floats2half2_rn(c, d);
-    return make_uint2(*reinterpret_cast<const uint32_t *>(&p), *reinterpret_cast<const uint32_t *>(&q));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
 }
-
-// Split a float4 (columns 4 * chunk ... + 3 of `row`) into TF32-exact high parts and residuals and store the operand
-// tiles at their swizzled positions.  TC_MIXED: hi_tile gets the float32 high parts (times S for the query side), x_tile
-// the fp16 row [S lo | hi] (queries) or [hi | S lo] (database): K columns 0-31 and 32-63 of the cross-term GEMM.
-// !TC_MIXED: x_tile gets the float32 residuals.
-template <bool QUERY>
-__device__ __forceinline__ void tc_store_split(unsigned char *hi_tile, unsigned char *x_tile, int row, int chunk, float4 v)
+__device__ __forceinline__ void tc_bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
-    const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
-    float4 h;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-    if (TC_MIXED) {
-        const float s = QUERY ? TC_SCALE : 1.f;
-        *reinterpret_cast<float4 *>(hi_tile + off) = make_float4(h.x * s, h.y * s, h.z * s, h.w * s);
-        const uint2 ph = tc_pack_half4(h.x, h.y, h.z, h.w);
-        const uint2 pl = tc_pack_half4((v.x - h.x) * TC_SCALE, (v.y - h.y) * TC_SCALE, (v.z - h.z) * TC_SCALE,
-                                       (v.w - h.w) * TC_SCALE);
-        // 8 halves per 16-byte chunk: columns 4 * chunk ... are the (chunk & 1) half of chunk (chunk >> 1), + 4 for K 32-63
-        const uint32_t o0 = (uint32_t)(row * 128 + (((chunk >> 1) ^ (row & 7)) << 4) + ((chunk & 1) << 3));
-        const uint32_t o1 = (uint32_t)(row * 128 + (((4 + (chunk >> 1)) ^ (row & 7)) << 4) + ((chunk & 1) << 3));
-        *reinterpret_cast<uint2 *>(x_tile + o0) = QUERY ? pl : ph;
-        *reinterpret_cast<uint2 *>(x_tile + o1) = QUERY ? ph : pl;
-    } else {
-        *reinterpret_cast<float4 *>(hi_tile + off) = h;
-        *reinterpret_cast<float4 *>(x_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-    }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(tc_smem_u32(bar)) : "memory");
 }
 
 // 32 accumulator columns of this thread's TMEM lane -> bit j set when column j passes the threshold
@@ -313,7 +301,7 @@ __device__ __forceinline__ uint32_t tc_bits32(const uint32_t (&w)[32], float thr
 
 inline size_t topk_tc_smem_bytes(int k)
 {
-    return (size_t)(4 + 2 * TC_STAGES) * TC_ROWS * 128 + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 12 + 128;
+    return (size_t)(2 + TC_STAGES) * TC_TILE_BYTES + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 12 + 128;
 }
 
 // DIM > 0: the embedding dimension is a compile-time constant (all loads of the exact dot product in flight at
@@ -324,17 +312,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     const TopkParams &p = pp.base;
     extern __shared__ __align__(1024) unsigned char tc_raw[];     // the 128-byte swizzle pattern repeats every 1024 bytes
     if (tc_smem_u32(tc_raw) & 1023u) __trap();
-    unsigned char *a_hi = tc_raw;                                 // [2][128 rows x 128 B]
-    unsigned char *a_lo = a_hi + 2 * TC_ROWS * 128;
-    unsigned char *b_hi = a_lo + 2 * TC_ROWS * 128;               // [TC_STAGES][128 x 128 B]
-    unsigned char *b_lo = b_hi + TC_STAGES * TC_ROWS * 128;
-    double *s_ls = reinterpret_cast<double *>(b_lo + TC_STAGES * TC_ROWS * 128);     // [k][256]
+    unsigned char *a_x = tc_raw;                                  // [2][16 KB]: query rows 0-127, 128-255
+    unsigned char *b_x = a_x + 2 * TC_TILE_BYTES;                 // [TC_STAGES][16 KB]
+    double *s_ls = reinterpret_cast<double *>(b_x + TC_STAGES * TC_TILE_BYTES);      // [k][256]
     double *s_sc = s_ls + (size_t)p.k * TC_QT;                                       // [TC_FIFO][256] scores of the pending rows
     int32_t *s_li = reinterpret_cast<int32_t *>(s_sc + (size_t)TC_FIFO * TC_QT);     // [k][256]
     int32_t *s_fifo = s_li + (size_t)p.k * TC_QT;                                    // [TC_FIFO][256] pending candidate rows
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_fifo + TC_FIFO * TC_QT);         // 8-byte aligned
     uint64_t *full_b = bars, *empty_b = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *a_full = acc_empty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dim = DIM > 0 ? DIM : p.dim;
@@ -345,22 +332,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     if (r_end > p.ndb) r_end = p.ndb;
     const int64_t n_tiles = (r_end - r_begin + TC_ROWS - 1) / TC_ROWS;
 
-    // ---- set-up: query tiles (split, swizzled), barriers, TMEM ----------------------------------
-    for (int c = tid; c < TC_QT * 8; c += TC_THREADS) {
-        const int row = c >> 3, chunk = c & 7, a = row >> 7;
-        const float4 v = *reinterpret_cast<const float4 *>(pp.qf + ((size_t)(q0 + row) * TC_KPAD + chunk * 4));
-        tc_store_split<true>(a_hi + a * TC_ROWS * 128, a_lo + a * TC_ROWS * 128, row & 127, chunk, v);
-    }
+    // ---- set-up: barriers, TMEM (the operand tiles arrive by bulk copy) ---------------------------
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { tc_mbar_init(&full_b[s], TC_PROD_THREADS); tc_mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < TC_STAGES; s++) { tc_mbar_init(&full_b[s], 1); tc_mbar_init(&empty_b[s], 1); }
         for (int b = 0; b < 2; b++) { tc_mbar_init(&acc_full[b], 1); tc_mbar_init(&acc_empty[b], TC_EPI_THREADS / 32); }
+        tc_mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == TC_THREADS / 32 - 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    asm volatile("fence.proxy.async.shared::cta;");               // the A tiles were written through the generic proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -589,8 +571,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
                 if (lane == 0) TC_TRACE(t, 10 + warp);
                 released = true;
+#ifdef DSPX_TC_EXPERIMENT_NOSCAN         // timing only (results are wrong): TMEM read-out and hand-off without the scan
+                const float t0 = __uint_as_float(v0[5] ^ v1[9] ^ v2[17] ^ v3[31]), t1 = t0, t2 = t0, t3 = t0;
+                any_hit = __any_sync(0xffffffffu, t >= 4 ? (t0 == 123.456f) : (t0 > thr32));
+#else
                 const float t0 = tc_top32(v0), t1 = tc_top32(v1), t2 = tc_top32(v2), t3 = tc_top32(v3);
                 any_hit = __any_sync(0xffffffffu, fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) > thr32);
+#endif
                 if (any_hit) {
                     if (__any_sync(0xffffffffu, t0 > thr32)) m[0] = tc_bits32(v0, thr32);
                     if (__any_sync(0xffffffffu, t1 > thr32)) m[1] = tc_bits32(v1, thr32);
@@ -643,51 +630,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 if (p.score_out) p.score_out[o + e] = have ? ls[(size_t)e * TC_QT] : -INFINITY;
             }
         }
-    } else if (tid < TC_EPI_THREADS + TC_PROD_THREADS) {
-        // ===== producers: database tile -> hi / lo operand tiles =====
-        // A tile is 16 KB and a load takes ~1 us to return: every thread keeps its 16 float4 of the NEXT tile in
-        // flight while it waits for the stage to be released (Little's law: less than a tile in flight starves
-        // the tensor core).
-        const int ptid = tid - TC_EPI_THREADS;
-        constexpr int PER = TC_ROWS * 8 / TC_PROD_THREADS;         // 16 chunks of 16 bytes per thread
-        float4 v[PER];
-        auto fetch = [&](int64_t t) {
-            const float4 *src = reinterpret_cast<const float4 *>(pp.dbf + (size_t)(r_begin + t * TC_ROWS) * TC_KPAD);
-#pragma unroll
-            for (int i = 0; i < PER; i++) v[i] = __ldg(src + ptid + i * TC_PROD_THREADS);
-        };
-        if (n_tiles > 0) fetch(0);
+    } else if (warp == TC_EPI_THREADS / 32) {
+        // ===== bulk copies: one thread =====
+        // The operand images were written by normalize_rows_split16_kernel in the layout the tensor core reads, so a tile is
+        // one 16 KB cp.async.bulk; TC_STAGES tiles are in flight (a copy takes ~1 us to land, a tile lasts ~0.5 us).
+        if (lane == 0) {
 #ifdef DSPX_TC_PROFILE
-        long long tc_prof_local[16] = {0};
+            long long tc_prof_local[16] = {0};
 #endif
-        TC_PROF_T0();
-        for (int64_t t = 0; t < n_tiles; t++) {
-            const int s = (int)(t % TC_STAGES);
-            tc_mbar_wait(&empty_b[s], (uint32_t)(((t / TC_STAGES) & 1) ^ 1));
-            TC_PROF_ADD(3);
-            unsigned char *hi = b_hi + s * TC_ROWS * 128, *lo = b_lo + s * TC_ROWS * 128;
-#pragma unroll
-            for (int i = 0; i < PER; i++) {
-                const int c = ptid + i * TC_PROD_THREADS;
-                tc_store_split<false>(hi, lo, c >> 3, c & 7, v[i]);
+            tc_mbar_expect_tx(a_full, 2 * TC_TILE_BYTES);
+            tc_bulk_load(a_x, pp.qx + (size_t)blockIdx.x * 2 * TC_TILE_BYTES, 2 * TC_TILE_BYTES, a_full);
+            const unsigned char *src = pp.dbx + (size_t)(r_begin / TC_ROWS) * TC_TILE_BYTES;
+            TC_PROF_T0();
+            for (int64_t t = 0; t < n_tiles; t++) {
+                const int s = (int)(t % TC_STAGES);
+                tc_mbar_wait(&empty_b[s], (uint32_t)(((t / TC_STAGES) & 1) ^ 1));
+                TC_PROF_ADD(3);
+                tc_mbar_expect_tx(&full_b[s], TC_TILE_BYTES);
+                tc_bulk_load(b_x + s * TC_TILE_BYTES, src + (size_t)t * TC_TILE_BYTES, TC_TILE_BYTES, &full_b[s]);
+                TC_PROF_ADD(4);
             }
-            asm volatile("fence.proxy.async.shared::cta;");
-            tc_mbar_arrive(&full_b[s]);
-            if (t + 1 < n_tiles) fetch(t + 1);
-            TC_PROF_ADD(4);
-        }
 #ifdef DSPX_TC_PROFILE
-        if (ptid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { tc_prof[3] = tc_prof_local[3]; tc_prof[4] = tc_prof_local[4]; }
+            if (blockIdx.x == 0 && blockIdx.y == 0) { tc_prof[3] = tc_prof_local[3]; tc_prof[4] = tc_prof_local[4]; }
 #endif
+        }
     } else if (lane == 0) {
         // ===== tensor-core issue: one thread =====
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc16 = (1u << 4) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32
-        (void)idesc16;
+        // kind::f16: fp16 x fp16 -> float32 (formats 0, 0; accumulator format 1), N = 128, M = 128, both operands K-major
+        const uint32_t idesc16 = (1u << 4) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 #ifdef DSPX_TC_PROFILE
         long long tc_prof_local[16] = {0};
         const long long tc_start = clock64();
 #endif
+        tc_mbar_wait(a_full, 0);                                   // the query tiles have landed
         TC_PROF_T0();
         for (int64_t t = 0; t < n_tiles; t++) {
             const int s = (int)(t % TC_STAGES), buf = (int)(t & 1);
@@ -697,23 +672,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             tc_mbar_wait(&full_b[s], (uint32_t)((t / TC_STAGES) & 1));
             TC_PROF_ADD(1);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint64_t bh = tc_desc(b_hi + s * TC_ROWS * 128), bl = tc_desc(b_lo + s * TC_ROWS * 128);
+            // a 128-byte row holds K = 64 halves [S hi | S lo]: +2 per K = 16 step (32 bytes) in descriptor units, +4 = the lo half
+            const uint64_t bd = tc_desc(b_x + s * TC_TILE_BYTES);
 #pragma unroll
             for (int a = 0; a < 2; a++) {
-                const uint64_t ah = tc_desc(a_hi + a * TC_ROWS * 128), al = tc_desc(a_lo + a * TC_ROWS * 128);
+                const uint64_t ad = tc_desc(a_x + a * TC_TILE_BYTES);
                 const uint32_t d = tmem + (uint32_t)(buf * 2 * TC_ROWS + a * TC_ROWS);
-                if (TC_MIXED) {
-                    // both cross terms as one fp16 GEMM of K = 64 (4 x K 16; 32 bytes per step like TF32's K 8), then S A_hi B_hi
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) tc_mma_f16(d, al + 2 * kk, bl + 2 * kk, idesc16, kk > 0);   // small terms first
-                } else {
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, al + 2 * kk, bh + 2 * kk, idesc, kk > 0);    // small terms first
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
-                }
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) tc_mma_tf32(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+                tc_mma_f16(d, ad + 4, bd, idesc16, 0);             // A_lo B_hi   (small terms first)
+                tc_mma_f16(d, ad + 6, bd + 2, idesc16, 1);
+                tc_mma_f16(d, ad, bd + 4, idesc16, 1);             // A_hi B_lo
+                tc_mma_f16(d, ad + 2, bd + 6, idesc16, 1);
+                tc_mma_f16(d, ad, bd, idesc16, 1);                 // A_hi B_hi
+                tc_mma_f16(d, ad + 2, bd + 2, idesc16, 1);
             }
             tc_commit(&empty_b[s]);                                // smem stage free once these MMAs have read it
             tc_commit(&acc_full[buf]);                             // accumulators complete

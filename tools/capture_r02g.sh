@@ -23,6 +23,37 @@ for sp in 5 9 11 13; do DSPX_TOPK_SPLITS=$sp timeout 120 python benchmarks/retr_
 if [ -f gpurun_scratch/libdspx_prof.so ]; then
   DSPX_LIBRARY=$PWD/gpurun_scratch/libdspx_prof.so timeout 300 python benchmarks/retr_tc_roles_steady.py > $OUT/r02g_roles_steady.txt 2>&1; echo "roles rc=$?"; cat $OUT/r02g_roles_steady.txt
 fi
+elif [ "$PART" = f16 ]; then
+# all-fp16 split + bulk-copy operands: error micro-benchmark, retrieval tests, timings, steady-state roles
+timeout 60 benchmarks/micro/umma_f16x > $OUT/r02h_umma_f16x.txt 2>&1; echo "umma_f16x rc=$?"; grep "status\|max err" $OUT/r02h_umma_f16x.txt | sort | uniq -c | sort -rn | head -30
+timeout 600 python -m pytest tests -m gpu -x -q -k "retrieval or topk or sharded or pipeline or embed" > $OUT/r02h_gputest_retr.log 2>&1; echo "retrieval gpu tests rc=$?"; tail -5 $OUT/r02h_gputest_retr.log
+timeout 300 python benchmarks/retr_quick.py > $OUT/r02h_retr_quick.txt 2>&1; echo "quick rc=$?"; cat $OUT/r02h_retr_quick.txt
+timeout 120 python benchmarks/retr_time.py 2>&1 | tail -1 > $OUT/r02h_retr_time.txt; cat $OUT/r02h_retr_time.txt
+for sp in 5 9 11 13; do DSPX_TOPK_SPLITS=$sp timeout 120 python benchmarks/retr_time.py 2>&1 | tail -1 | sed "s/^/splits $sp: /" >> $OUT/r02h_retr_splits.txt; done; cat $OUT/r02h_retr_splits.txt
+for f in gpurun_scratch/libdspx_prof*.so; do
+  [ -f $f ] || continue
+  echo "## $f (DSPX_EXPERIMENT_KEEP_THR=1: calls 1, 2 are steady state)" >> $OUT/r02h_roles_keepthr.txt
+  DSPX_EXPERIMENT_KEEP_THR=1 DSPX_LIBRARY=$PWD/$f timeout 300 python benchmarks/retr_tc_roles_steady.py >> $OUT/r02h_roles_keepthr.txt 2>&1
+done
+cat $OUT/r02h_roles_keepthr.txt
+elif [ "$PART" = var ]; then
+# tuning variants: every gpurun_scratch/libdspx_<name>.so except the profiling build; then the steady-state role profile
+: > $OUT/r02g_variants.txt
+echo "## default library" >> $OUT/r02g_variants.txt
+timeout 300 python benchmarks/retr_quick.py >> $OUT/r02g_variants.txt 2>&1
+for f in gpurun_scratch/libdspx_*.so; do
+  name=$(basename $f .so); name=${name#libdspx_}
+  case $name in prof*) continue;; esac
+  echo "## $name" >> $OUT/r02g_variants.txt
+  DSPX_LIBRARY=$PWD/$f timeout 300 python benchmarks/retr_quick.py >> $OUT/r02g_variants.txt 2>&1
+done
+cat $OUT/r02g_variants.txt
+for f in gpurun_scratch/libdspx_prof*.so; do
+  [ -f $f ] || continue
+  echo "## $f (DSPX_EXPERIMENT_KEEP_THR=1: calls 1, 2 are steady state)" >> $OUT/r02g_roles_keepthr.txt
+  DSPX_EXPERIMENT_KEEP_THR=1 DSPX_LIBRARY=$PWD/$f timeout 300 python benchmarks/retr_tc_roles_steady.py >> $OUT/r02g_roles_keepthr.txt 2>&1
+done
+cat $OUT/r02g_roles_keepthr.txt
 else
 python -m pytest tests -m gpu -x -q > $OUT/r02g_gputest.log 2>&1; echo "gpu tests rc=$?"; tail -2 $OUT/r02g_gputest.log
 python bench.py > $OUT/r02g_bench_1gpu.log 2> $OUT/r02g_bench_1gpu.err; echo "bench rc=$?"
@@ -31,4 +62,4 @@ python bench.py $BENCH_ARGS > $OUT/r02g_bench_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/r02g_launches_raw.csv python bench.py $BENCH_ARGS > $OUT/r02g_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cosine_topk_tc_kernel -c 1 -o $OUT/r02g_topk_tc -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_topk.log 2>&1
 fi
-ls -la $OUT | grep r02g
+ls -la $OUT | grep 'r02[gh]'
