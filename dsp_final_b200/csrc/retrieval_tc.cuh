@@ -17,12 +17,16 @@
 // range (S hi <= 2048, S lo < 2; a value only turns subnormal below 2^-25 of the norm, where even flushing it to zero costs
 // < 1.5e-7 in total) and the accumulator holds S^2 * score; the scan compares against S^2 * threshold.  The three terms are
 // K slices of the same two rows:  A[32..63] x B[0..31]  (lo hi),  A[0..31] x B[32..63]  (hi lo),  A[0..31] x B[0..31]  (hi hi).
-// fp16 rounds lo to 11 bits (error <= 2^-22 |v|; TF32 truncated it: 2^-21).  What is dropped is A_lo B_lo and that rounding,
-// each below 2^-20 |q_i d_i|, i.e. 2.9e-6 in total since sum |q_i d_i| <= 1 for unit vectors; rounding the inputs to float32
-// adds 1.2e-7 and the float32 accumulation at most 1.4e-6: 4.5e-6 worst case.  Measured against float64
-// (benchmarks/micro/umma_f16x.cu, profiles/r02_micro_umma_f16x.txt): <= 6.5e-7 on random, clustered and wide-dynamic-range
-// unit vectors and with adversarial mantissas (all 13 low bits set, all residuals of one sign; three TF32 passes: 1.2e-6).
-// TC_EPS = 8e-6, so every pair with s64 >= thr64 has s_tc > thr32 = float(thr64 - eps) and is re-scored.  eps only costs
+// Error budget for unit vectors (sum |q_i d_i| <= 1), worst case:
+//   inputs rounded to float32 (both sides)                                   2 * 2^-24          = 1.2e-7
+//   A_lo B_lo dropped                                                        2^-10 * 2^-10      = 9.5e-7
+//   lo rounded to 11 bits by fp16 (round to nearest: <= 2^-11 |lo|), 2 terms 2 * 2^-21          = 9.5e-7
+//   float32 accumulation in the tensor core, allowing every one of the 16 + 1 addends of the two hi x hi MMAs to lose
+//   2^-25 of the row's largest magnitude and a truncation of the accumulator per MMA          ~ 1.2e-6
+// = 3.2e-6.  Measured against float64 (benchmarks/micro/umma_f16x.cu, profiles/r02_micro_umma_f16x.txt): <= 6.5e-7 on
+// random, clustered and wide-dynamic-range unit vectors and with adversarial mantissas (all 13 low bits set, all residuals
+// of one sign; the three TF32 passes of round 1: 1.2e-6).  TC_EPS = 6e-6 (round 1: 8e-6 over a 4.5e-6 bound), so every
+// pair with s64 >= thr64 has s_tc > thr32 = float(thr64 - eps) and is re-scored.  eps only costs
 // extra re-scores: on tightly clustered embeddings (every cosine near 1, thousands of rows within eps of the k-th score) the
 // kernel degrades towards the all-float64 kernel's time instead of failing.
 //
@@ -32,7 +36,7 @@
 // for every query tile with ordinary loads and stores (~1100 cycles per tile, as long as the MMAs themselves) and the epilogue
 // warps that shared their schedulers were the laggards the issue thread waited for (profiles/r02_topk_tc_mixed_ab.txt).
 //
-// Structure of a CTA (320 threads, one per SM), 256 queries x one database split:
+// Structure of a CTA (352 threads, one per SM), 256 queries x one database split:
 //   warps 0-7  epilogue: thread = one query.  All 128 scores of its accumulator row go to registers (four
 //              tcgen05.ld.32x32b.x32 in flight at once), the TMEM buffer is handed back to the tensor core at once, and
 //              only then are the scores compared with the thread's float threshold (3-input max tree per 32 columns, ONE vote
@@ -46,8 +50,10 @@
 //              re-scoring holds the pipeline up (the issue thread needs all eight warps to release a buffer).
 //   warp 8     one lane: bulk copies of the query tiles (once) and of the database tiles into a 4-stage ring; mbarrier
 //              expect_tx / complete_tx hand-off to the issue thread.
-//   warp 9     one lane issues 2 x 6 tcgen05.mma kind::f16 (M 128, N 128, K 16) per tile into a double-buffered
-//              512-column TMEM accumulator and commits to the mbarriers of the smem stage and the buffer.
+//   warps 9-10 one lane each: issues the 6 tcgen05.mma kind::f16 (M 128, N 128, K 16) of ITS query half (warps 0-3 / 4-7) per
+//              tile into that half's double-buffered TMEM accumulator (2 x 2 x 128 columns) and commits to the mbarriers of
+//              the smem stage (count 2) and of the buffer.  The halves are independent pipelines over the shared database
+//              ring: an issue thread waits for the slowest of four warps, not of eight.
 // Measured structure (profiles/r02_topk_tc_pipeline.md): the tensor core needs 1536 cycles per tile, the TMEM read-out
 // 400-450 (320 B/clk per SM, overlapping with the MMAs: benchmarks/micro/umma_ld_overlap.cu); what the issue thread
 // waited for in round 1 were the scans and re-scoring passes of the slowest of the eight warps.
@@ -65,10 +71,13 @@ constexpr int TC_QT = 256;            // queries per CTA: two 128-row A tiles
 constexpr int TC_ROWS = 128;          // database rows per tile (UMMA N)
 constexpr int TC_STAGES = 4;          // database tiles in flight (16 KB each)
 constexpr int TC_EPI_THREADS = 256;
-constexpr int TC_THREADS = TC_EPI_THREADS + 32 + 32;      // + bulk-copy warp + tensor-core issue warp
+constexpr int TC_THREADS = TC_EPI_THREADS + 32 + 64;      // + bulk-copy warp + two tensor-core issue warps (one per query half)
 constexpr int TC_KPAD = 32;           // padded embedding dimension: 32 hi + 32 lo halves = one 128-byte swizzle row
 constexpr int TC_TILE_BYTES = 128 * 128;                  // operand image of 128 rows
-constexpr double TC_EPS = 8e-6;
+#ifndef DSPX_TC_EPS
+#define DSPX_TC_EPS 6e-6
+#endif
+constexpr double TC_EPS = DSPX_TC_EPS;
 constexpr float TC_S = 2048.f;                            // operand scale S = 2^11
 constexpr float TC_SCALE = TC_S * TC_S;                   // the accumulator holds S^2 * score
 #ifndef DSPX_TC_TRIGGER_LANE
@@ -200,8 +209,10 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity)
         asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
 #else
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+        // the suspend-time hint lets the hardware park the thread instead of re-issuing the wait: the two single-thread
+        // roles share their schedulers with epilogue warps 0/4 and 1/5, which the issue thread ends up waiting for
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 #endif
         if (ok) return;
         if (spin > (1u << 28)) __trap();
@@ -301,7 +312,7 @@ __device__ __forceinline__ uint32_t tc_bits32(const uint32_t (&w)[32], float thr
 
 inline size_t topk_tc_smem_bytes(int k)
 {
-    return (size_t)(2 + TC_STAGES) * TC_TILE_BYTES + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 12 + 128;
+    return (size_t)(2 + TC_STAGES) * TC_TILE_BYTES + (size_t)TC_QT * k * 12 + (size_t)TC_FIFO * TC_QT * 12 + 256;    // + 17 mbarriers, TMEM slot
 }
 
 // DIM > 0: the embedding dimension is a compile-time constant (all loads of the exact dot product in flight at
@@ -319,8 +330,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     int32_t *s_li = reinterpret_cast<int32_t *>(s_sc + (size_t)TC_FIFO * TC_QT);     // [k][256]
     int32_t *s_fifo = s_li + (size_t)p.k * TC_QT;                                    // [TC_FIFO][256] pending candidate rows
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_fifo + TC_FIFO * TC_QT);         // 8-byte aligned
-    uint64_t *full_b = bars, *empty_b = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
-    uint64_t *a_full = acc_empty + 2;
+    // acc_full / acc_empty: [query half][buffer]
+    uint64_t *full_b = bars, *empty_b = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 4;
+    uint64_t *a_full = acc_empty + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -334,8 +346,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
 
     // ---- set-up: barriers, TMEM (the operand tiles arrive by bulk copy) ---------------------------
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { tc_mbar_init(&full_b[s], 1); tc_mbar_init(&empty_b[s], 1); }
-        for (int b = 0; b < 2; b++) { tc_mbar_init(&acc_full[b], 1); tc_mbar_init(&acc_empty[b], TC_EPI_THREADS / 32); }
+        for (int s = 0; s < TC_STAGES; s++) { tc_mbar_init(&full_b[s], 1); tc_mbar_init(&empty_b[s], 2); }    // both halves read a stage
+        for (int b = 0; b < 4; b++) { tc_mbar_init(&acc_full[b], 1); tc_mbar_init(&acc_empty[b], TC_EPI_THREADS / 64); }
         tc_mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -365,6 +377,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         double gthr = -INFINITY;
         unsigned long long genc = 0;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TC_ROWS);
+        // The two query halves (warps 0-3, 4-7) are separate pipelines: own accumulator barriers, own issue thread.  The
+        // issue thread waits for the slowest warp of ITS half only, so a warp that is re-scoring holds up three others
+        // instead of seven; the halves may drift apart by the depth of the smem ring.
+        uint64_t *my_full = acc_full + (warp >> 2) * 2, *my_empty = acc_empty + (warp >> 2) * 2;
         // Candidates wait in a small per-thread ring in shared memory and are re-scored in lock step, one per lane
         // and round: a round costs the same whether 1 or 32 lanes have work (it is bound by the latency of the
         // float64 row loads), so the ring is drained only when some lane has TC_FIFO_TRIGGER entries, which fills
@@ -509,7 +525,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             }
             return thr32c;
         };
-        if (gslot) genc = __ldcg(gslot);                           // what earlier CTAs of this query already reached
+        // The shared threshold is read one tile ahead: the load is issued when a tile arrives and consumed when the NEXT one
+        // does, so its L2 round trip never sits on the path of a warp that is behind (the issue thread waits for the slowest).
+        auto load_shared_thr = [&]() -> unsigned long long {
+            unsigned long long v = 0;
+            if (gslot) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(gslot) : "memory");
+            return v;
+        };
+        genc = load_shared_thr();                                  // what earlier CTAs of this query already reached
+        unsigned long long genc_next = genc;
 #ifdef DSPX_TC_PROFILE
         long long tc_prof_local[16] = {0};
 #endif
@@ -527,7 +551,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 for (uint32_t spin = 0;; spin++) {
                     uint32_t ok;                                   // test_wait: try_wait would sleep through the whole stall
                     asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                                 : "=r"(ok) : "r"(tc_smem_u32(&acc_full[buf])), "r"(parity) : "memory");
+                                 : "=r"(ok) : "r"(tc_smem_u32(&my_full[buf])), "r"(parity) : "memory");
                     if (__all_sync(0xffffffffu, ok != 0)) break;
                     if (spin > (1u << 28)) __trap();
                     if (!drained && __any_sync(0xffffffffu, f_cnt > 0 && clock64() - w0 > TC_IDLE_CYCLES)) {
@@ -540,6 +564,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             if (lane == 0) TC_TRACE(t, 2 + warp);
             __syncwarp();                                          // tcgen05.ld is warp-collective
             asm volatile("tcgen05.fence::after_thread_sync;");
+            genc = genc_next;
+            genc_next = load_shared_thr();                         // for the next tile
             if (genc) gthr = tc_dec(genc);
             const uint32_t acc = lane_base + (uint32_t)(buf * 2 * TC_ROWS);
             uint32_t m[4] = {0u, 0u, 0u, 0u};
@@ -568,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 tc_ld_wait(v3);
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
+                if (lane == 0) tc_mbar_arrive(&my_empty[buf]);
                 if (lane == 0) TC_TRACE(t, 10 + warp);
                 released = true;
 #ifdef DSPX_TC_EXPERIMENT_NOSCAN         // timing only (results are wrong): TMEM read-out and hand-off without the scan
@@ -588,10 +614,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
             if (!released) {
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);    // the tensor core may overwrite this buffer now
+                if (lane == 0) tc_mbar_arrive(&my_empty[buf]);    // the tensor core may overwrite this buffer now
                 if (lane == 0) TC_TRACE(t, 10 + warp);
             }
-            if (gslot) genc = __ldcg(gslot);                       // for the next tile: in flight during the re-scoring below
             TC_PROF_ADD(6);
 #ifdef DSPX_TC_EXPERIMENT_NODRAIN
             t_nodrain_skip = t >= 4;
@@ -655,43 +680,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
 #endif
         }
     } else if (lane == 0) {
-        // ===== tensor-core issue: one thread =====
+        // ===== tensor-core issue: one thread per query half =====
         // kind::f16: fp16 x fp16 -> float32 (formats 0, 0; accumulator format 1), N = 128, M = 128, both operands K-major
         const uint32_t idesc16 = (1u << 4) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const int a = warp - (TC_EPI_THREADS / 32 + 1);             // 0: queries 0-127, 1: queries 128-255
+        uint64_t *my_full = acc_full + a * 2, *my_empty = acc_empty + a * 2;
 #ifdef DSPX_TC_PROFILE
         long long tc_prof_local[16] = {0};
         const long long tc_start = clock64();
 #endif
         tc_mbar_wait(a_full, 0);                                   // the query tiles have landed
+        const uint64_t ad = tc_desc(a_x + a * TC_TILE_BYTES);
         TC_PROF_T0();
         for (int64_t t = 0; t < n_tiles; t++) {
             const int s = (int)(t % TC_STAGES), buf = (int)(t & 1);
-            tc_mbar_wait(&acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
+            tc_mbar_wait(&my_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
             TC_PROF_ADD(0);
-            TC_TRACE(t, 0);
+            if (a == 0) TC_TRACE(t, 0);
             tc_mbar_wait(&full_b[s], (uint32_t)((t / TC_STAGES) & 1));
             TC_PROF_ADD(1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             // a 128-byte row holds K = 64 halves [S hi | S lo]: +2 per K = 16 step (32 bytes) in descriptor units, +4 = the lo half
             const uint64_t bd = tc_desc(b_x + s * TC_TILE_BYTES);
-#pragma unroll
-            for (int a = 0; a < 2; a++) {
-                const uint64_t ad = tc_desc(a_x + a * TC_TILE_BYTES);
-                const uint32_t d = tmem + (uint32_t)(buf * 2 * TC_ROWS + a * TC_ROWS);
-                tc_mma_f16(d, ad + 4, bd, idesc16, 0);             // A_lo B_hi   (small terms first)
-                tc_mma_f16(d, ad + 6, bd + 2, idesc16, 1);
-                tc_mma_f16(d, ad, bd + 4, idesc16, 1);             // A_hi B_lo
-                tc_mma_f16(d, ad + 2, bd + 6, idesc16, 1);
-                tc_mma_f16(d, ad, bd, idesc16, 1);                 // A_hi B_hi
-                tc_mma_f16(d, ad + 2, bd + 2, idesc16, 1);
-            }
-            tc_commit(&empty_b[s]);                                // smem stage free once these MMAs have read it
-            tc_commit(&acc_full[buf]);                             // accumulators complete
+            const uint32_t d = tmem + (uint32_t)(buf * 2 * TC_ROWS + a * TC_ROWS);
+            tc_mma_f16(d, ad + 4, bd, idesc16, 0);                 // A_lo B_hi   (small terms first)
+            tc_mma_f16(d, ad + 6, bd + 2, idesc16, 1);
+            tc_mma_f16(d, ad, bd + 4, idesc16, 1);                 // A_hi B_lo
+            tc_mma_f16(d, ad + 2, bd + 6, idesc16, 1);
+            tc_mma_f16(d, ad, bd, idesc16, 1);                     // A_hi B_hi
+            tc_mma_f16(d, ad + 2, bd + 2, idesc16, 1);
+            tc_commit(&empty_b[s]);                                // smem stage free once both halves' MMAs have read it
+            tc_commit(&my_full[buf]);                              // this half's accumulators complete
             TC_PROF_ADD(2);
-            TC_TRACE(t, 1);
+            if (a == 0) TC_TRACE(t, 1);
         }
 #ifdef DSPX_TC_PROFILE
-        if (blockIdx.x == 0 && blockIdx.y == 0) { for (int i = 0; i < 3; i++) tc_prof[i] = tc_prof_local[i]; tc_prof[9] = clock64() - tc_start; }
+        if (a == 0 && blockIdx.x == 0 && blockIdx.y == 0) { for (int i = 0; i < 3; i++) tc_prof[i] = tc_prof_local[i]; tc_prof[9] = clock64() - tc_start; }
 #endif
     }
 

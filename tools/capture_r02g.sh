@@ -36,6 +36,20 @@ for f in gpurun_scratch/libdspx_prof*.so; do
   DSPX_EXPERIMENT_KEEP_THR=1 DSPX_LIBRARY=$PWD/$f timeout 300 python benchmarks/retr_tc_roles_steady.py >> $OUT/r02h_roles_keepthr.txt 2>&1
 done
 cat $OUT/r02h_roles_keepthr.txt
+elif [ "$PART" = seed ]; then
+# threshold seed: retrieval tests, size sweep (DSPX_TOPK_SEED_TILES, 0 = off), three shapes with and without
+timeout 600 python -m pytest tests -m gpu -x -q -k "retrieval or topk or sharded or pipeline or embed" > $OUT/r02i_gputest_retr.log 2>&1; echo "retrieval gpu tests rc=$?"; tail -3 $OUT/r02i_gputest_retr.log
+for sd in 0 16 32 64 128 256; do DSPX_TOPK_SEED_TILES=$sd timeout 120 python benchmarks/retr_time.py 2>&1 | tail -1 | sed "s/^/seed tiles $sd: /" >> $OUT/r02i_seed_sweep.txt; done; cat $OUT/r02i_seed_sweep.txt
+echo "## default (64 seed tiles)" > $OUT/r02i_retr_quick.txt; timeout 300 python benchmarks/retr_quick.py >> $OUT/r02i_retr_quick.txt 2>&1
+echo "## DSPX_TOPK_SEED_TILES=0" >> $OUT/r02i_retr_quick.txt; DSPX_TOPK_SEED_TILES=0 timeout 300 python benchmarks/retr_quick.py >> $OUT/r02i_retr_quick.txt 2>&1
+echo "## DSPX_TOPK_SEED_TILES=256" >> $OUT/r02i_retr_quick.txt; DSPX_TOPK_SEED_TILES=256 timeout 300 python benchmarks/retr_quick.py >> $OUT/r02i_retr_quick.txt 2>&1
+cat $OUT/r02i_retr_quick.txt
+for f in gpurun_scratch/libdspx_prof*.so; do
+  [ -f $f ] || continue
+  echo "## $f, cold calls (first-wave CTA (0, 0) after the seed launch)" >> $OUT/r02i_roles.txt
+  DSPX_LIBRARY=$PWD/$f timeout 300 python benchmarks/retr_tc_roles_steady.py 2>&1 | grep "^call" >> $OUT/r02i_roles.txt
+done
+cat $OUT/r02i_roles.txt
 elif [ "$PART" = var ]; then
 # tuning variants: every gpurun_scratch/libdspx_<name>.so except the profiling build; then the steady-state role profile
 : > $OUT/r02g_variants.txt
@@ -62,4 +76,4 @@ python bench.py $BENCH_ARGS > $OUT/r02g_bench_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/r02g_launches_raw.csv python bench.py $BENCH_ARGS > $OUT/r02g_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cosine_topk_tc_kernel -c 1 -o $OUT/r02g_topk_tc -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_topk.log 2>&1
 fi
-ls -la $OUT | grep 'r02[gh]'
+ls -la $OUT | grep 'r02[ghi]'
