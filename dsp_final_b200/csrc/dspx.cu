@@ -876,6 +876,7 @@ size_t dspx_cosine_topk_workspace(int64_t nq, int64_t ndb, int dim, int k)
     b += align256((size_t)((nq + TC_QT - 1) / TC_QT) * TC_QT * TC_KPAD * 4);
     b += align256((size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4);
     b += align256((size_t)nq * 8);                                                // thresholds shared between splits
+    b += align256((size_t)((nq + TC_QT - 1) / TC_QT) * TK_MAX_SPLITS * 4);      // per (query tile, split): lists written
     return b + 1024;
 }
 
@@ -910,6 +911,8 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
     const size_t dbf_bytes = (size_t)((ndb + TK_ROWS - 1) / TK_ROWS) * TK_ROWS * TC_KPAD * 4;
     ws += align256(dbf_bytes);
     unsigned long long *shared_thr = reinterpret_cast<unsigned long long *>(ws);
+    ws += align256((size_t)nq * 8);
+    int *split_done = reinterpret_cast<int *>(ws);
     // Filter kernels (single-chunk dimensions, lists that fit beside the tiles), all with exact float64 re-scoring:
     // tensor-core (split fp16) filter, else packed-FP32 filter, else the all-float64 kernel.  DSPX_TOPK = tc | f32 | f64 forces one.
     const TopkKnobs &knobs = topk_knobs();
@@ -994,6 +997,8 @@ int dspx_cosine_topk(const void *q_dev, int64_t nq, const void *db_dev, int64_t 
             cp.qx = reinterpret_cast<const unsigned char *>(qf_t);
             cp.dbx = reinterpret_cast<const unsigned char *>(dbf_t);
             cp.shared_thr = tp.n_splits > 1 ? shared_thr : nullptr;
+            cp.done = tp.n_splits > 1 ? split_done : nullptr;
+            if (cp.done) DSPX_CUDA_CHECK(cudaMemsetAsync(split_done, 0, (size_t)qtiles * tp.n_splits * 4, st));
 #ifdef DSPX_TC_PROFILE                  // profiling builds only: DSPX_EXPERIMENT_KEEP_THR=1 keeps the thresholds of the previous call (steady-state per-role cycles)
             if (cp.shared_thr && !getenv("DSPX_EXPERIMENT_KEEP_THR"))
 #else

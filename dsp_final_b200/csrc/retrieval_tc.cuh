@@ -177,6 +177,7 @@ struct TopkTcParams {
     const unsigned char *qx;    // fp16 operand tiles of the queries: [ceil(nq / 256) * 2][16 KB] (normalize_rows_split16_kernel)
     const unsigned char *dbx;   // fp16 operand tiles of the database: [ceil(ndb / 128)][16 KB]
     unsigned long long *shared_thr;   // [nq] order-encoded k-th scores shared by the splits of a query (null: one split)
+    int *done;                        // [query tiles][n_splits] set once a CTA's lists are in idx_out / score_out (null: one split)
 };
 
 // order-preserving double <-> uint64 (0 is below every double): lets atomicMax maintain a shared threshold
@@ -391,6 +392,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         bool t_nodrain_skip = false;
 #endif
         int32_t *fifo = s_fifo + ql;
+        // One exactly scored row into the thread's list.  Rows reach a list in an order in which every entry already there
+        // with the same score has a lower index (own rows: increasing index; rows taken over from finished splits: see below).
+        auto insert_row = [&](double s, int32_t row) {
+            if (s < gthr) return;                          // below another split's k-th score
+            if (cnt == k && !(s > thr)) return;            // ties with the current worst keep the lower index
+            // the list is unordered while it runs: overwrite the worst entry, then find the new worst with k
+            // independent loads (a sorted insert would be a dependent load-compare-store chain per position)
+            const int pos = cnt < k ? cnt : wpos;
+            ls[(size_t)pos * TC_QT] = s;
+            li[(size_t)pos * TC_QT] = row;
+            if (cnt < k) cnt++;
+            thr_dirty = true;
+            if (cnt == k) {
+                double w = INFINITY, w1 = INFINITY;       // two independent scans (even / odd entries)
+                int32_t wi = -1, wi1 = -1;
+                int wp = 0, wp1 = 0;
+                int e = 0;
+                for (; e + 1 < k; e += 2) {
+                    const double v = ls[(size_t)e * TC_QT], v1 = ls[(size_t)(e + 1) * TC_QT];
+                    const int32_t vi = li[(size_t)e * TC_QT], vi1 = li[(size_t)(e + 1) * TC_QT];
+                    if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
+                    if (v1 < w1 || (v1 == w1 && vi1 > wi1)) { w1 = v1; wi1 = vi1; wp1 = e + 1; }
+                }
+                if (e < k) {
+                    const double v = ls[(size_t)e * TC_QT];
+                    const int32_t vi = li[(size_t)e * TC_QT];
+                    if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
+                }
+                if (w1 < w || (w1 == w && wi1 > wi)) { w = w1; wp = wp1; }
+                thr = w;
+                wpos = wp;
+                if (gslot && thr > gthr) atomicMax(gslot, tc_enc(thr));
+            }
+        };
         // Re-scoring is shared by the warp: the pending rows of all 32 queries form one work list (prefix sum of the ring
         // fill counts), lane i scores item i of it -- any query's row, the exact left-to-right float64 fma chain -- and
         // leaves the score next to the ring entry; then every lane inserts its own rows in order.  A scoring pass costs
@@ -450,36 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                     const double s = s_sc[(size_t)slot * TC_QT + ql];
                     f_head++;
                     f_cnt--;
-                    if (s < gthr) continue;                        // below another split's k-th score
-                    if (cnt == k && !(s > thr)) continue;          // ties with the current worst keep the lower index
-                    // the list is unordered while it runs: overwrite the worst entry, then find the new worst with k
-                    // independent loads (a sorted insert would be a dependent load-compare-store chain per position)
-                    const int pos = cnt < k ? cnt : wpos;
-                    ls[(size_t)pos * TC_QT] = s;
-                    li[(size_t)pos * TC_QT] = (int32_t)row;
-                    if (cnt < k) cnt++;
-                    thr_dirty = true;
-                    if (cnt == k) {
-                        double w = INFINITY, w1 = INFINITY;       // two independent scans (even / odd entries)
-                        int32_t wi = -1, wi1 = -1;
-                        int wp = 0, wp1 = 0;
-                        int e = 0;
-                        for (; e + 1 < k; e += 2) {
-                            const double v = ls[(size_t)e * TC_QT], v1 = ls[(size_t)(e + 1) * TC_QT];
-                            const int32_t vi = li[(size_t)e * TC_QT], vi1 = li[(size_t)(e + 1) * TC_QT];
-                            if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
-                            if (v1 < w1 || (v1 == w1 && vi1 > wi1)) { w1 = v1; wi1 = vi1; wp1 = e + 1; }
-                        }
-                        if (e < k) {
-                            const double v = ls[(size_t)e * TC_QT];
-                            const int32_t vi = li[(size_t)e * TC_QT];
-                            if (v < w || (v == w && vi > wi)) { w = v; wi = vi; wp = e; }
-                        }
-                        if (w1 < w || (w1 == w && wi1 > wi)) { w = w1; wp = wp1; }
-                        thr = w;
-                        wpos = wp;
-                        if (gslot && thr > gthr) atomicMax(gslot, tc_enc(thr));
-                    }
+                    insert_row(s, (int32_t)row);
                 }
                 __syncwarp();
             }
@@ -534,6 +540,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
         };
         genc = load_shared_thr();                                  // what earlier CTAs of this query already reached
         unsigned long long genc_next = genc;
+        if (genc) gthr = tc_dec(genc);
+        // Take over the lists of the splits of this query tile that have already finished (CTAs are dispatched in order
+        // of their linear index, so these are lower splits: lower row indices).  A split's own k-th score says little about
+        // the final one -- with s splits it sits near rank s * k of the whole database, and shared_thr, the best of those,
+        // let ~7x the necessary rows through -- but the k-th score over everything ranked so far is as tight as a bound
+        // can be.  The foreign rows only serve as the threshold: they are left out when the list is written (their own
+        // split reported them), and an own row they displace has k better rows ahead of it in the database.
+        if (pp.done && split > 0) {
+            for (int j = 0; j < split; j++) {
+                int fin;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fin) : "l"(pp.done + (size_t)blockIdx.x * p.n_splits + j) : "memory");
+                if (!__all_sync(0xffffffffu, fin != 0)) continue;
+                if (!active) continue;
+                const size_t o = ((size_t)gq * p.n_splits + j) * k;
+                for (int e = 0; e < k; e++) {
+                    const int32_t fi = __ldcg(p.idx_out + o + e);
+                    if (fi < 0) break;                             // lists are written compacted, best first
+                    insert_row(__ldcg(p.score_out + o + e), fi);
+                }
+            }
+            __syncwarp();
+        }
 #ifdef DSPX_TC_PROFILE
         long long tc_prof_local[16] = {0};
 #endif
@@ -649,12 +677,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
                 }
             }
             const size_t o = ((size_t)gq * p.n_splits + split) * k;
-            for (int e = 0; e < k; e++) {
-                const bool have = e < cnt;
-                p.idx_out[o + e] = have ? li[(size_t)e * TC_QT] : -1;
-                if (p.score_out) p.score_out[o + e] = have ? ls[(size_t)e * TC_QT] : -INFINITY;
+            int w = 0;
+            for (int e = 0; e < cnt; e++) {                        // rows taken over from other splits are not reported twice
+                const int32_t ri = li[(size_t)e * TC_QT];
+                if (ri < r_begin || ri >= r_end) continue;
+                p.idx_out[o + w] = ri;
+                if (p.score_out) p.score_out[o + w] = ls[(size_t)e * TC_QT];
+                w++;
+            }
+            for (; w < k; w++) {
+                p.idx_out[o + w] = -1;
+                if (p.score_out) p.score_out[o + w] = -INFINITY;
             }
         }
+        if (pp.done) __threadfence();                              // the lists, before the flag below
     } else if (warp == TC_EPI_THREADS / 32) {
         // ===== bulk copies: one thread =====
         // The operand images were written by normalize_rows_split16_kernel in the layout the tensor core reads, so a tile is
@@ -722,6 +758,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cosine_topk_tc_kernel(const Top
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     __syncwarp();
+    if (pp.done && tid == 0)
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(pp.done + (size_t)blockIdx.x * p.n_splits + split), "r"(1) : "memory");
     if (warp == TC_THREADS / 32 - 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
