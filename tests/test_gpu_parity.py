@@ -329,6 +329,37 @@ def test_retrieval_duplicates_across_splits(torch_cuda):
         assert np.array_equal(sc, want_sc), k
 
 
+def test_retrieval_takeover_across_waves(torch_cuda):
+    """More CTAs than SMs (40 query tiles x several splits): CTAs of later waves take over the lists of the splits of their
+    query tile that have already finished (retrieval_tc.cuh) and report only their own rows.  The database is ordered so
+    that every later split displaces what the earlier ones found (scores grow with the index), the best row of every query
+    has exact copies at both ends of the index range (ties across splits: lowest index first), and a block of queries has
+    its whole top-k inside the FIRST split (later CTAs then insert nothing and must still not report the rows they took over)."""
+    from dsp_final_b200 import retrieval as R
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(2024)
+    nq, ndb, dim, k = 40 * 256, 200_000, 26, 20
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    base = rng.standard_normal((ndb, dim)).astype(np.float32)
+    # rows lean more and more towards a common direction the queries share: cosines rise with the index
+    common = rng.standard_normal(dim).astype(np.float32)
+    q += 0.8 * common
+    db = base + (np.linspace(0.0, 1.5, ndb, dtype=np.float32)[:, None] * common)
+    sel = np.arange(0, nq, 160)                            # 64 queries checked against the oracle (all query tiles)
+    for j, qi in enumerate(sel[:24]):                      # exact copies of a near-query row at both ends and in the middle
+        row = (q[qi] * 2.0 + 0.01 * rng.standard_normal(dim)).astype(np.float32)
+        db[[50 + j, 100_000 + j, ndb - 50 - j]] = row
+    for j, qi in enumerate(sel[24:40]):                    # whole top-k in the first 2000 rows
+        rows = 200 + j * 100 + np.arange(k + 4)
+        db[rows] = (q[qi][None, :] * rng.uniform(1.0, 3.0, (k + 4, 1)) + 1e-3 * rng.standard_normal((k + 4, dim))).astype(np.float32)
+    idx, sc = R.cosine_topk(q, db, k, return_scores=True)
+    want_idx, want_sc = O.cosine_topk(q[sel], db, k, return_scores=True)
+    assert np.array_equal(np.asarray(idx)[sel], want_idx)
+    assert np.array_equal(np.asarray(sc)[sel], want_sc)
+    assert (np.asarray(idx) >= 0).all() and all(len(set(r)) == k for r in np.asarray(idx)[::97])   # complete lists, no row twice
+
+
 def test_retrieval_fuzz_filter_kernels(torch_cuda):
     """Randomised shapes and adversarial score distributions through the tensor-core filter path (dim <= 32,
     k <= 24 on the tcgen05 kernel, k = 28 on the float32 filter): indices and scores must equal the oracle's bit for bit every time."""

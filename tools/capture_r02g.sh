@@ -75,5 +75,7 @@ python bench.py --impl reference > $OUT/r02g_bench_reference.log 2> $OUT/r02g_be
 python bench.py $BENCH_ARGS > $OUT/r02g_bench_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/r02g_launches_raw.csv python bench.py $BENCH_ARGS > $OUT/r02g_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cosine_topk_tc_kernel -c 1 -o $OUT/r02g_topk_tc -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_topk.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:feat_warp8_kernel -s 3 -c 1 -o $OUT/r02g_feat_warp8 -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_feat.log 2>&1
+python benchmarks/retr_quick.py > $OUT/r02g_retr_quick_final.txt 2>&1
 fi
 ls -la $OUT | grep 'r02[ghi]'
