@@ -2,6 +2,7 @@
 # One-GPU A/B of the retrieval filter's mixed TF32 + fp16 split (last session of round 2):
 #   gpurun -- 'bash tools/capture_r02g.sh ab'      error micro-benchmark, retrieval GPU tests, retr_quick on three libraries
 #   gpurun -- 'bash tools/capture_r02g.sh final'   whole GPU suite, bench lines, launch list, ncu of the retrieval kernel
+#   gpurun -- 'bash tools/capture_r02g.sh final_b' ncu of the feature kernel, frame x hop sweep
 # The A/B libraries live in gpurun_scratch/ (git-ignored, travels with the snapshot): libdspx_head.so = the previous
 # commit, libdspx_mixed_4vote.so = mixed split with the per-block votes, libdspx_prof.so = -DDSPX_TC_PROFILE.
 set -u
@@ -68,14 +69,18 @@ for f in gpurun_scratch/libdspx_prof*.so; do
   DSPX_EXPERIMENT_KEEP_THR=1 DSPX_LIBRARY=$PWD/$f timeout 300 python benchmarks/retr_tc_roles_steady.py >> $OUT/r02g_roles_keepthr.txt 2>&1
 done
 cat $OUT/r02g_roles_keepthr.txt
-else
+elif [ "$PART" = final ]; then
+# gpurun brings back at most 64 MiB: one ncu --set full report per call (final = retrieval kernel, final_b = feature kernel)
 python -m pytest tests -m gpu -x -q > $OUT/r02g_gputest.log 2>&1; echo "gpu tests rc=$?"; tail -2 $OUT/r02g_gputest.log
 python bench.py > $OUT/r02g_bench_1gpu.log 2> $OUT/r02g_bench_1gpu.err; echo "bench rc=$?"
 python bench.py --impl reference > $OUT/r02g_bench_reference.log 2> $OUT/r02g_bench_reference.err; echo "reference arm rc=$?"
 python bench.py $BENCH_ARGS > $OUT/r02g_bench_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/r02g_launches_raw.csv python bench.py $BENCH_ARGS > $OUT/r02g_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cosine_topk_tc_kernel -c 1 -o $OUT/r02g_topk_tc -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_topk.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:feat_warp8_kernel -s 3 -c 1 -o $OUT/r02g_feat_warp8 -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_feat.log 2>&1
 python benchmarks/retr_quick.py > $OUT/r02g_retr_quick_final.txt 2>&1
+else
+python bench.py $BENCH_ARGS > $OUT/r02g_bench_plain_b.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:feat_warp8_kernel -s 3 -c 1 -o $OUT/r02g_feat_warp8 -f python bench.py $BENCH_ARGS > $OUT/r02g_ncu_feat.log 2>&1
+python benchmarks/bench_extra.py --sweep --logmel128 --clips 1000 > $OUT/r02g_bench_extra.jsonl 2>&1
 fi
 ls -la $OUT | grep 'r02[ghi]'
