@@ -303,12 +303,19 @@ __device__ __forceinline__ float tc_top32(const uint32_t (&w)[32])
     const float t2 = fmaxf(fmaxf(mx[6], mx[7]), mx[8]), t3 = fmaxf(mx[9], mx[10]);
     return fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
 }
+// Bit j set when column j passes.  thr - v is negative exactly when v > thr (equal gives +0; an empty list has
+// thr = -inf: everything passes; an inactive lane +inf: nothing does), so the mask is the sign bits: one FADD (FMA pipe)
+// and one funnel shift per column, in four independent chains -- the compare / select / add form cost 2.5 ALU-pipe
+// instructions per column, and the ALU pipe (max tree, masks, ring bookkeeping) is this kernel's busiest.
 __device__ __forceinline__ uint32_t tc_bits32(const uint32_t (&w)[32], float thr32)
 {
     uint32_t part[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int j = 0; j < 32; j++) part[j & 3] |= (__uint_as_float(w[j]) > thr32) ? (1u << j) : 0u;
-    return (part[0] | part[1]) | (part[2] | part[3]);
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int j = 7; j >= 0; j--)                               // highest column first: column 8 c + j ends up at bit j
+            part[c] = __funnelshift_l(__float_as_uint(thr32 - __uint_as_float(w[8 * c + j])), part[c], 1);
+    return (part[0] | (part[1] << 8)) | ((part[2] << 16) | (part[3] << 24));
 }
 
 inline size_t topk_tc_smem_bytes(int k)
