@@ -47,16 +47,20 @@
 //              so "strictly better than the current worst" keeps ties at the lower index; ordered once at the end).
 //              Re-scoring happens when a ring is full, when the warp holds 64 pending rows, or -- preferably -- while
 //              the warp would otherwise wait more than TC_IDLE_CYCLES for the next tile, i.e. while another warp's
-//              re-scoring holds the pipeline up (the issue thread needs all eight warps to release a buffer).
+//              re-scoring holds the pipeline up (an issue thread needs all four warps of its half to release a buffer).
 //   warp 8     one lane: bulk copies of the query tiles (once) and of the database tiles into a 4-stage ring; mbarrier
 //              expect_tx / complete_tx hand-off to the issue thread.
 //   warps 9-10 one lane each: issues the 6 tcgen05.mma kind::f16 (M 128, N 128, K 16) of ITS query half (warps 0-3 / 4-7) per
 //              tile into that half's double-buffered TMEM accumulator (2 x 2 x 128 columns) and commits to the mbarriers of
 //              the smem stage (count 2) and of the buffer.  The halves are independent pipelines over the shared database
 //              ring: an issue thread waits for the slowest of four warps, not of eight.
-// Measured structure (profiles/r02_topk_tc_pipeline.md): the tensor core needs 1536 cycles per tile, the TMEM read-out
-// 400-450 (320 B/clk per SM, overlapping with the MMAs: benchmarks/micro/umma_ld_overlap.cu); what the issue thread
-// waited for in round 1 were the scans and re-scoring passes of the slowest of the eight warps.
+// Measured structure (profiles/r02_topk_tc_takeover.txt, r02_topk_tc_pipeline.md): the tensor core needs 768 cycles per tile
+// (1536 with the three TF32 passes of round 1), the TMEM read-out 400-450 (320 B/clk per SM, overlapping with the MMAs:
+// benchmarks/micro/umma_ld_overlap.cu); a tile without candidates takes a warp ~1470 cycles (two warps per scheduler:
+// latency-bound), and a CTA of the first wave, whose lists start empty, ~3500: every sparse re-scoring pass of one warp
+// stalls the other three of its half after two tiles.  The number of candidates is fixed by the scan order
+// (k (1 + ln(n / k)) per query), so seeding thresholds from a sample or giving the first wave short splits only moves that
+// work around (profiles/r02_topk_tc_seed_join_experiments.txt); what later CTAs gain comes from taking finished lists over.
 #pragma once
 
 #include <cuda_fp16.h>
